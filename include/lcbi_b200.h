@@ -1,0 +1,69 @@
+/* lcbi_b200 — C ABI of the B200-native token-mixing hot path of NHLBI/long_context_biomedical_imaging.
+ *
+ * The reference is pure Python: its "plugin boundary" for this path is the nn.Module seam
+ * (SABlock.forward, WindowAttention.forward / SwinTransformerBlock.forward_part1, MONAI patch embedding).
+ * This header is what a Python (ctypes / torch extension) binding of those seams calls; every entry point
+ * cites the reference code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch's caching allocator); the library
+ *     borrows them for the duration of the enqueue and allocates nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no internal synchronisation;
+ *   - return value: LCBI_OK (0) or a negative lcbi_status; lcbi_last_error() gives the text
+ *     (thread-local). Functions never throw and never fall back to a CPU path;
+ *   - strides are in ELEMENTS, ordered (batch, row/token, head); the innermost head_dim is contiguous.
+ */
+#ifndef LCBI_B200_H_
+#define LCBI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum lcbi_status {
+  LCBI_OK = 0,
+  LCBI_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, misaligned pointer/stride */
+  LCBI_ERR_UNSUPPORTED = -2,  /* shape outside what the sm_100a kernels implement (e.g. head_dim) */
+  LCBI_ERR_CUDA = -3,         /* CUDA runtime error (text in lcbi_last_error) */
+  LCBI_ERR_TENSOR_MAP = -4,   /* cuTensorMapEncodeTiled rejected the view */
+  LCBI_ERR_WORKSPACE = -5     /* workspace too small */
+} lcbi_status;
+
+#define LCBI_B200_VERSION 100 /* 0.1.0 */
+
+int lcbi_version(void);
+const char* lcbi_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense (ViT global) attention core.  Replaces model/models/backbone_vit.py:191-201
+ * (einsum q k^T * scale -> softmax -> einsum with v), reading q/k/v in place from the qkv Linear output
+ * laid out (B, N, 3, H, d) (the "b h (qkv l d)" rearrange at backbone_vit.py:168) and writing
+ * (B, N, H*d) (the "b h l d -> b l (h d)" rearrange at :169,201).
+ *   q: (B,Nq,H,d) view, k/v: (B,Nk,H,d) views, o: (B,Nq,H,d) view — bf16; lse: (B,H,Nq) fp32, natural log
+ *   of sum_j exp(scale*q.k_j) per row (needed by the backward and by ring-attention merging).
+ *   head_dim must be 64 (every ViT preset of the reference: backbone_vit.py:56-76).
+ * ---------------------------------------------------------------------------------------------- */
+int lcbi_dense_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq,
+                        int Nk, int head_dim, const int64_t* q_strides, const int64_t* k_strides,
+                        const int64_t* v_strides, const int64_t* o_strides, float scale, void* stream);
+
+/* Backward of the above (what autograd derives for backbone_vit.py:191-201).
+ *   d_o, o: (B,Nq,H,d) bf16 views; dq: (B,Nq,H,d), dk/dv: (B,Nk,H,d) bf16 views.
+ *   accumulate_dkv != 0: dk/dv are instead fp32 (B,Nk,H,d) CONTIGUOUS buffers that are accumulated into
+ *   (ring sequence-parallel steps); their stride arguments are ignored.
+ *   workspace: at least lcbi_dense_attn_bwd_workspace_bytes() bytes, 128-byte aligned. */
+size_t lcbi_dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
+int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                        const float* lse, void* dq, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
+                        const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
+                        const int64_t* o_strides, const int64_t* do_strides, const int64_t* dq_strides,
+                        const int64_t* dk_strides, const int64_t* dv_strides, float scale, int accumulate_dkv,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCBI_B200_H_ */

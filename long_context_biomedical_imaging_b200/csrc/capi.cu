@@ -1,0 +1,96 @@
+// extern "C" entry points declared in include/lcbi_b200.h: argument checking + dispatch to the launchers.
+#include <cstdio>
+#include <cstring>
+
+#include "lcbi_kernels.h"
+
+namespace lcbi {
+
+static thread_local char g_err[512] = "";
+
+void set_error_text(const char* msg) {
+  std::strncpy(g_err, msg, sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+int set_cuda_error(cudaError_t e) {
+  if (e == cudaSuccess) return LCBI_OK;
+  std::snprintf(g_err, sizeof(g_err), "CUDA error %d: %s", static_cast<int>(e), cudaGetErrorString(e));
+  return LCBI_ERR_CUDA;
+}
+
+static int fail(int code, const char* msg) {
+  set_error_text(msg);
+  return code;
+}
+
+static void copy3(int64_t* dst, const int64_t* src) {
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = src[2];
+}
+
+}  // namespace lcbi
+
+using namespace lcbi;
+
+extern "C" {
+
+int lcbi_version(void) { return LCBI_B200_VERSION; }
+
+const char* lcbi_last_error(void) { return g_err; }
+
+int lcbi_dense_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq,
+                        int Nk, int head_dim, const int64_t* q_strides, const int64_t* k_strides,
+                        const int64_t* v_strides, const int64_t* o_strides, float scale, void* stream) {
+  if (!q || !k || !v || !o || !lse || !q_strides || !k_strides || !v_strides || !o_strides)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_fwd: null pointer argument");
+  DenseAttnArgs a;
+  a.q = q; a.k = k; a.v = v; a.o = o; a.lse = lse;
+  a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.head_dim = head_dim;
+  copy3(a.q_strides, q_strides); copy3(a.k_strides, k_strides);
+  copy3(a.v_strides, v_strides); copy3(a.o_strides, o_strides);
+  a.scale = scale;
+  int rc = dense_attn_fwd_launch(a, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_UNSUPPORTED) return fail(rc, "lcbi_dense_attn_fwd: only head_dim == 64 is implemented");
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_dense_attn_fwd: bad size, or pointer/stride not 16-byte aligned");
+  if (rc == LCBI_ERR_TENSOR_MAP) return fail(rc, "lcbi_dense_attn_fwd: TMA tensor map encode failed");
+  return rc;
+}
+
+size_t lcbi_dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim) {
+  return dense_attn_bwd_workspace_bytes(B, H, Nq, head_dim);
+}
+
+int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                        const float* lse, void* dq, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
+                        const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
+                        const int64_t* o_strides, const int64_t* do_strides, const int64_t* dq_strides,
+                        const int64_t* dk_strides, const int64_t* dv_strides, float scale, int accumulate_dkv,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !workspace || !q_strides || !k_strides ||
+      !v_strides || !o_strides || !do_strides || !dq_strides)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_bwd: null pointer argument");
+  if (!accumulate_dkv && (!dk_strides || !dv_strides))
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_bwd: dk/dv strides required unless accumulate_dkv");
+  DenseAttnBwdArgs a;
+  a.q = q; a.k = k; a.v = v; a.o = o; a.d_o = d_o; a.lse = lse;
+  a.dq = dq; a.dk = dk; a.dv = dv;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.head_dim = head_dim;
+  copy3(a.q_strides, q_strides); copy3(a.k_strides, k_strides); copy3(a.v_strides, v_strides);
+  copy3(a.o_strides, o_strides); copy3(a.do_strides, do_strides); copy3(a.dq_strides, dq_strides);
+  const int64_t contiguous[3] = {static_cast<int64_t>(Nk) * H * head_dim, static_cast<int64_t>(H) * head_dim, head_dim};
+  copy3(a.dk_strides, accumulate_dkv ? contiguous : dk_strides);
+  copy3(a.dv_strides, accumulate_dkv ? contiguous : dv_strides);
+  a.scale = scale;
+  a.accumulate_dkv = accumulate_dkv;
+  int rc = dense_attn_bwd_launch(a, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_UNSUPPORTED) return fail(rc, "lcbi_dense_attn_bwd: only head_dim == 64 is implemented");
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_dense_attn_bwd: bad size, or pointer/stride not 16-byte aligned");
+  if (rc == LCBI_ERR_TENSOR_MAP) return fail(rc, "lcbi_dense_attn_bwd: TMA tensor map encode failed");
+  if (rc == LCBI_ERR_WORKSPACE) return fail(rc, "lcbi_dense_attn_bwd: workspace too small or misaligned");
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,553 @@
+// Dense (ViT global) attention backward for sm_100a, head_dim 64, bf16 in / fp32 accumulate.
+//
+// Gradient of the reference's SABlock attention core (/root/reference/model/models/backbone_vit.py:191-201,
+// what autograd derives from einsum -> *scale -> softmax -> einsum) computed flash-style: S and P are
+// recomputed per tile from q, k and the forward's log-sum-exp, nothing N x N is stored.
+//
+// Three launches:
+//   bwd_prep      D[b,h,i] = sum_d dO*O ; lse2 = lse*log2(e) (rows padded to the 128-row tile get +inf / 0)
+//   bwd_main      one CTA = one 128-key tile of one (batch, head); loops over 128-row query tiles.
+//                 dK, dV accumulate in TMEM over the loop; each tile's dQ partial is reduced into an fp32
+//                 accumulator with a TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32).
+//   bwd_finish    dq = bf16(scale * dq_accum)
+//
+// bwd_main per query tile i (all five GEMMs on tcgen05, accumulators in TMEM, transposed formulation so that
+// the softmax threads own KEY rows and P^T / dS^T come out in the layout the next GEMM wants):
+//   S^T  = K  Q_i^T      A = K  (smem, K-major)        B = Q_i  (smem, K-major)      -> TMEM [0,128)
+//   dP^T = V  dO_i^T     A = V  (smem, K-major)        B = dO_i (smem, K-major)      -> TMEM [128,256)
+//   P^T  = exp2(S^T*c - lse2[q])            (bf16, written to TMEM [448,512))
+//   dS^T = P^T o (dP^T - D[q])              (bf16, written to a swizzled smem tile)
+//   dV  += P^T  dO_i     A = P^T (TMEM)                B = dO_i (smem, MN-major)     -> TMEM [256,320)
+//   dK  += dS^T Q_i      A = dS^T (smem, K-major)      B = Q_i  (smem, MN-major)     -> TMEM [320,384)
+//   dQ_i = dS   K        A = dS^T (smem, MN-major)     B = K    (smem, MN-major)     -> TMEM [384,448)
+// Warp roles (512 threads): warps 0-7 exponentiate / form dS (thread = key row x 64 query columns),
+// warps 8-11 drain dQ_i (TMEM -> swizzled fp32 smem -> TMA reduce-add), warp 12 TMA producer,
+// warp 13 UMMA issuer. Register file is rebalanced with setmaxnreg.
+#include "lcbi_kernels.h"
+#include "sm100_ptx.cuh"
+#include "tma_host.h"
+
+namespace lcbi {
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kHeadDim = 64;
+constexpr int kTileBytes = kTile * kHeadDim * 2;  // 16 KB
+constexpr int kNumThreads = 512;
+constexpr float kLog2e = 1.4426950408889634f;
+
+constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemP = 448;
+
+struct __align__(1024) BwdSmem {
+  uint8_t k[kTileBytes];
+  uint8_t v[kTileBytes];
+  uint8_t q[2][kTileBytes];      // also dK staging in the epilogue
+  uint8_t dout[2][kTileBytes];   // also dV staging in the epilogue
+  uint8_t ds[2 * kTileBytes];    // dS^T: two [128 keys x 64 queries] bf16 SW128 atoms
+  uint8_t dq_stage[2 * kTileBytes];  // two [128 queries x 32 fp32] SW128 tiles
+  float lse2[2][kTile];
+  float dsum[2][kTile];
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2], do_full[2], do_empty[2];
+  uint64_t s_full, dp_full, p_full, ds_full, ds_empty, dq_full, dq_empty, dkv_full;
+  uint32_t tmem_base;
+};
+
+struct BwdParams {
+  int B, H, Nq, Nk, Nq_pad;
+  float scale, scale_log2;
+  const float* lse2;   // (B,H,Nq_pad)
+  const float* dsum;   // (B,H,Nq_pad)
+  int accumulate_dkv;
+};
+
+#ifndef LCBI_BWD_SETMAXNREG
+#define LCBI_BWD_SETMAXNREG 0
+#endif
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+#if LCBI_BWD_SETMAXNREG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+#if LCBI_BWD_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: D = rowsum(dO o O), lse2 = lse * log2e; one warp per (b, h, row)
+// ------------------------------------------------------------------------------------------------
+__global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                const float* __restrict__ lse, float* __restrict__ lse2, float* __restrict__ dsum,
+                                int B, int H, int Nq, int Nq_pad, int64_t o_sb, int64_t o_sr, int64_t o_sh,
+                                int64_t do_sb, int64_t do_sr, int64_t do_sh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t total = static_cast<int64_t>(B) * H * Nq_pad;
+  if (warp_global >= total) return;
+  const int row = static_cast<int>(warp_global % Nq_pad);
+  const int h = static_cast<int>((warp_global / Nq_pad) % H);
+  const int b = static_cast<int>(warp_global / (static_cast<int64_t>(Nq_pad) * H));
+  if (row >= Nq) {
+    if (lane == 0) {
+      lse2[warp_global] = INFINITY;   // exp2(x - inf) = 0: padded query columns contribute nothing
+      dsum[warp_global] = 0.f;
+    }
+    return;
+  }
+  const __nv_bfloat162 ov =
+      *reinterpret_cast<const __nv_bfloat162*>(o + b * o_sb + row * o_sr + h * o_sh + lane * 2);
+  const __nv_bfloat162 dv =
+      *reinterpret_cast<const __nv_bfloat162*>(d_o + b * do_sb + row * do_sr + h * do_sh + lane * 2);
+  float acc = __bfloat162float(ov.x) * __bfloat162float(dv.x) + __bfloat162float(ov.y) * __bfloat162float(dv.y);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    dsum[warp_global] = acc;
+    lse2[warp_global] = lse[(static_cast<int64_t>(b) * H + h) * Nq + row] * kLog2e;
+  }
+}
+
+// dq = bf16(scale * dq_accum); one thread = 8 consecutive elements of one (b, row, h)
+__global__ void bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int H, int Nq,
+                                  int64_t sb, int64_t sr, int64_t sh, float scale) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * Nq * H * (kHeadDim / 8);
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % (kHeadDim / 8));
+  const int h = static_cast<int>((idx / (kHeadDim / 8)) % H);
+  const int row = static_cast<int>((idx / (kHeadDim / 8) / H) % Nq);
+  const int b = static_cast<int>(idx / (kHeadDim / 8) / H / Nq);
+  const float4 a0 = *reinterpret_cast<const float4*>(acc + idx * 8);
+  const float4 a1 = *reinterpret_cast<const float4*>(acc + idx * 8 + 4);
+  uint4 out;
+  out.x = pack_bf16x2(a0.x * scale, a0.y * scale);
+  out.y = pack_bf16x2(a0.z * scale, a0.w * scale);
+  out.z = pack_bf16x2(a1.x * scale, a1.y * scale);
+  out.w = pack_bf16x2(a1.z * scale, a1.w * scale);
+  *reinterpret_cast<uint4*>(dq + b * sb + row * sr + h * sh + c8 * 8) = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// main
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNumThreads, 1)
+dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                      const __grid_constant__ CUtensorMap tm_dqacc, const __grid_constant__ CUtensorMap tm_dk,
+                      const __grid_constant__ CUtensorMap tm_dv, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int kv_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int kv_base = kv_tile * kTile;
+  const int n_q = p.Nq_pad / kTile;
+
+  if (tid == 0) {
+    mbar_init(&sm.kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.q_full[s], 1);
+      mbar_init(&sm.q_empty[s], 1);
+      mbar_init(&sm.do_full[s], 1);
+      mbar_init(&sm.do_empty[s], 1);
+    }
+    mbar_init(&sm.s_full, 1);
+    mbar_init(&sm.dp_full, 1);
+    mbar_init(&sm.p_full, 256);
+    mbar_init(&sm.ds_full, 256);
+    mbar_init(&sm.ds_empty, 1);
+    mbar_init(&sm.dq_full, 1);
+    mbar_init(&sm.dq_empty, 128);
+    mbar_init(&sm.dkv_full, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 13) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp >= 12) {
+    setmaxnreg_dec<40>();
+    if (warp == 12) {
+      // ---------------------------------------------------------------- TMA producer
+      if (elect_one()) {
+        mbar_expect_tx(&sm.kv_full, 2 * kTileBytes);
+        tma_load_4d(sm.k, &tm_k, &sm.kv_full, 0, head, kv_base, batch);
+        tma_load_4d(sm.v, &tm_v, &sm.kv_full, 0, head, kv_base, batch);
+        const float* lse_row = p.lse2 + (static_cast<size_t>(batch) * p.H + head) * p.Nq_pad;
+        const float* ds_row = p.dsum + (static_cast<size_t>(batch) * p.H + head) * p.Nq_pad;
+        for (int i = 0; i < n_q; ++i) {
+          const int st = i & 1;
+          const uint32_t ph = (i >> 1) & 1;
+          mbar_wait(&sm.q_empty[st], ph ^ 1);
+          mbar_expect_tx(&sm.q_full[st], kTileBytes + 2 * kTile * 4);
+          tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, i * kTile, batch);
+          bulk_load_1d(sm.lse2[st], lse_row + i * kTile, kTile * 4, &sm.q_full[st]);
+          bulk_load_1d(sm.dsum[st], ds_row + i * kTile, kTile * 4, &sm.q_full[st]);
+          mbar_wait(&sm.do_empty[st], ph ^ 1);
+          mbar_expect_tx(&sm.do_full[st], kTileBytes);
+          tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, i * kTile, batch);
+        }
+      }
+    } else if (warp == 13) {
+      // ---------------------------------------------------------------- UMMA issuer
+      if (elect_one()) {
+        constexpr uint32_t idesc_nt = make_idesc_bf16(kTile, kTile, 0, 0);     // S^T, dP^T
+        constexpr uint32_t idesc_kmn = make_idesc_bf16(kTile, kHeadDim, 0, 1); // dV, dK: A K-major, B MN-major
+        constexpr uint32_t idesc_mnmn = make_idesc_bf16(kTile, kHeadDim, 1, 1);// dQ: A MN-major, B MN-major
+        const uint32_t k_addr = smem_u32(sm.k), v_addr = smem_u32(sm.v), ds_addr = smem_u32(sm.ds);
+        const uint32_t q_addr[2] = {smem_u32(sm.q[0]), smem_u32(sm.q[1])};
+        const uint32_t do_addr[2] = {smem_u32(sm.dout[0]), smem_u32(sm.dout[1])};
+
+        auto gemm_nt = [&](uint32_t d_col, uint32_t a_addr, uint32_t b_addr) {
+#pragma unroll
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)
+            umma_ss(tmem + d_col, make_smem_desc(a_addr + kk * 32, 16, 1024, kLayoutSW128),
+                    make_smem_desc(b_addr + kk * 32, 16, 1024, kLayoutSW128), idesc_nt, kk > 0 ? 1u : 0u);
+        };
+
+        mbar_wait(&sm.kv_full, 0);
+        mbar_wait(&sm.q_full[0], 0);
+        tc_fence_after();
+        gemm_nt(kTmemS, k_addr, q_addr[0]);
+        umma_commit(&sm.s_full);
+        mbar_wait(&sm.do_full[0], 0);
+        tc_fence_after();
+        gemm_nt(kTmemDP, v_addr, do_addr[0]);
+        umma_commit(&sm.dp_full);
+
+        for (int i = 0; i < n_q; ++i) {
+          const int st = i & 1, nst = st ^ 1;
+          const uint32_t nph = ((i + 1) >> 1) & 1;
+          const bool more = (i + 1) < n_q;
+
+          // dV += P^T dO_i
+          mbar_wait(&sm.p_full, i & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < kTile / 16; ++kk)
+            umma_ts(tmem + kTmemDV, tmem + kTmemP + kk * 8,
+                    make_smem_desc(do_addr[st] + kk * 2048, 16, 1024, kLayoutSW128), idesc_kmn,
+                    (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&sm.do_empty[st]);
+          // S^T(i+1)
+          if (more) {
+            mbar_wait(&sm.q_full[nst], nph);
+            tc_fence_after();
+            gemm_nt(kTmemS, k_addr, q_addr[nst]);
+            umma_commit(&sm.s_full);
+          }
+          // dK += dS^T Q_i
+          mbar_wait(&sm.ds_full, i & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < kTile / 16; ++kk)
+            umma_ss(tmem + kTmemDK,
+                    make_smem_desc(ds_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128),
+                    make_smem_desc(q_addr[st] + kk * 2048, 16, 1024, kLayoutSW128), idesc_kmn,
+                    (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&sm.q_empty[st]);
+          // dQ_i = dS K
+          mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < kTile / 16; ++kk)
+            umma_ss(tmem + kTmemDQ, make_smem_desc(ds_addr + kk * 2048, kTileBytes, 1024, kLayoutSW128),
+                    make_smem_desc(k_addr + kk * 2048, 16, 1024, kLayoutSW128), idesc_mnmn, kk > 0 ? 1u : 0u);
+          umma_commit(&sm.dq_full);
+          umma_commit(&sm.ds_empty);
+          // dP^T(i+1)
+          if (more) {
+            mbar_wait(&sm.do_full[nst], nph);
+            tc_fence_after();
+            gemm_nt(kTmemDP, v_addr, do_addr[nst]);
+            umma_commit(&sm.dp_full);
+          }
+        }
+        umma_commit(&sm.dkv_full);
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ dQ drain (warps 8-11)
+    setmaxnreg_dec<96>();
+    const int row = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t t_dq = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kTmemDQ;
+    const bool issuer = (tid == 8 * 32);
+    for (int i = 0; i < n_q; ++i) {
+      mbar_wait(&sm.dq_full, i & 1);
+      tc_fence_after();
+      uint32_t r[64];
+      tmem_ld_x32(t_dq, r);
+      tmem_ld_x32(t_dq + 32, r + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sm.dq_empty);
+      if (issuer) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tiles
+      named_bar_sync(3, 128);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {          // 16-byte chunk c of the 256-byte fp32 row
+        uint4 val = make_uint4(r[c * 4], r[c * 4 + 1], r[c * 4 + 2], r[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(sm.dq_stage + (c >> 3) * kTileBytes + sw128_offset(row, c & 7)) = val;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(4, 128);
+      if (issuer) {
+        tma_reduce_add_4d(&tm_dqacc, sm.dq_stage, 0, head, i * kTile, batch);
+        tma_reduce_add_4d(&tm_dqacc, sm.dq_stage + kTileBytes, 32, head, i * kTile, batch);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  } else {
+    // ------------------------------------------------------------------ P^T / dS^T (warps 0-7)
+    setmaxnreg_inc<184>();
+    const int hh = warp >> 2;                   // which 64-query half of the tile this thread handles
+    const int row = (warp & 3) * 32 + lane;     // key row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const float c = p.scale_log2;
+
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      float pr[64];
+      // ---- phase A: P^T = exp2(S^T * c - lse2[q])
+      mbar_wait(&sm.q_full[st], ph);   // lse2 / dsum of this tile visible
+      mbar_wait(&sm.s_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t s[32];
+        tmem_ld_x32(tmem + lane_sel + kTmemS + hh * 64 + ch * 32, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 l4 = *reinterpret_cast<const float4*>(&sm.lse2[st][hh * 64 + ch * 32 + g * 4]);
+          const float e0 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 0]), c, -l4.x));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 1]), c, -l4.y));
+          const float e2 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 2]), c, -l4.z));
+          const float e3 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 3]), c, -l4.w));
+          pr[ch * 32 + g * 4 + 0] = e0;
+          pr[ch * 32 + g * 4 + 1] = e1;
+          pr[ch * 32 + g * 4 + 2] = e2;
+          pr[ch * 32 + g * 4 + 3] = e3;
+          pk[g * 2] = pack_bf16x2(e0, e1);
+          pk[g * 2 + 1] = pack_bf16x2(e2, e3);
+        }
+        tmem_st_x16(tmem + lane_sel + kTmemP + hh * 32 + ch * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sm.p_full);
+
+      // ---- phase B: dS^T = P^T o (dP^T - D[q])
+      mbar_wait(&sm.dp_full, i & 1);
+      mbar_wait(&sm.ds_empty, (i & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t dp[32];
+        tmem_ld_x32(tmem + lane_sel + kTmemDP + hh * 64 + ch * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {         // 8 query columns -> one 16-byte chunk
+          const float4 d0 = *reinterpret_cast<const float4*>(&sm.dsum[st][hh * 64 + ch * 32 + g * 8]);
+          const float4 d1 = *reinterpret_cast<const float4*>(&sm.dsum[st][hh * 64 + ch * 32 + g * 8 + 4]);
+          const float* pp = &pr[ch * 32 + g * 8];
+          const uint32_t* dd = &dp[g * 8];
+          uint4 val;
+          val.x = pack_bf16x2(pp[0] * (__uint_as_float(dd[0]) - d0.x), pp[1] * (__uint_as_float(dd[1]) - d0.y));
+          val.y = pack_bf16x2(pp[2] * (__uint_as_float(dd[2]) - d0.z), pp[3] * (__uint_as_float(dd[3]) - d0.w));
+          val.z = pack_bf16x2(pp[4] * (__uint_as_float(dd[4]) - d1.x), pp[5] * (__uint_as_float(dd[5]) - d1.y));
+          val.w = pack_bf16x2(pp[6] * (__uint_as_float(dd[6]) - d1.z), pp[7] * (__uint_as_float(dd[7]) - d1.w));
+          *reinterpret_cast<uint4*>(sm.ds + hh * kTileBytes + sw128_offset(row, ch * 4 + g)) = val;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.ds_full);
+    }
+
+    // ---- epilogue: hh == 0 drains dV, hh == 1 drains dK (scaled)
+    mbar_wait(&sm.dkv_full, 0);
+    tc_fence_after();
+    uint32_t r[64];
+    const uint32_t t_src = tmem + lane_sel + (hh ? kTmemDK : kTmemDV);
+    tmem_ld_x32(t_src, r);
+    tmem_ld_x32(t_src + 32, r + 32);
+    tmem_ld_wait();
+    const float mul = hh ? p.scale : 1.0f;
+    uint8_t* stage = hh ? sm.q[0] : sm.dout[0];   // 32 KB each (both stages), free once every MMA retired
+    const CUtensorMap* tm = hh ? &tm_dk : &tm_dv;
+    if (!p.accumulate_dkv) {
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        uint4 val;
+        val.x = pack_bf16x2(__uint_as_float(r[c16 * 8 + 0]) * mul, __uint_as_float(r[c16 * 8 + 1]) * mul);
+        val.y = pack_bf16x2(__uint_as_float(r[c16 * 8 + 2]) * mul, __uint_as_float(r[c16 * 8 + 3]) * mul);
+        val.z = pack_bf16x2(__uint_as_float(r[c16 * 8 + 4]) * mul, __uint_as_float(r[c16 * 8 + 5]) * mul);
+        val.w = pack_bf16x2(__uint_as_float(r[c16 * 8 + 6]) * mul, __uint_as_float(r[c16 * 8 + 7]) * mul);
+        *reinterpret_cast<uint4*>(stage + sw128_offset(row, c16)) = val;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(5 + hh, 128);
+      if ((tid & 127) == 0) {
+        tma_store_4d(tm, stage, 0, head, kv_base, batch);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[cc * 4]) * mul),
+                               __float_as_uint(__uint_as_float(r[cc * 4 + 1]) * mul),
+                               __float_as_uint(__uint_as_float(r[cc * 4 + 2]) * mul),
+                               __float_as_uint(__uint_as_float(r[cc * 4 + 3]) * mul));
+        *reinterpret_cast<uint4*>(stage + (cc >> 3) * kTileBytes + sw128_offset(row, cc & 7)) = val;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(5 + hh, 128);
+      if ((tid & 127) == 0) {
+        tma_reduce_add_4d(tm, stage, 0, head, kv_base, batch);
+        tma_reduce_add_4d(tm, stage + kTileBytes, 32, head, kv_base, batch);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem, 512);
+}
+
+int make_bf16_map(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t* st) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(kHeadDim), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(st[2]) * 2, static_cast<uint64_t>(st[1]) * 2,
+                               static_cast<uint64_t>(st[0]) * 2};
+  const uint32_t box[4] = {kHeadDim, 1, kTile, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// fp32 (B, N, H, 64) contiguous accumulator, box = 32 floats (128 B) x 128 rows
+int make_f32_acc_map(CUtensorMap* m, const void* base, int B, int H, int N) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(kHeadDim), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(kHeadDim) * 4, static_cast<uint64_t>(H) * kHeadDim * 4,
+                               static_cast<uint64_t>(N) * H * kHeadDim * 4};
+  const uint32_t box[4] = {32, 1, kTile, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim) {
+  const size_t nq_pad = align_up(static_cast<size_t>(Nq), kTile);
+  const size_t acc = align_up(static_cast<size_t>(B) * Nq * H * head_dim * 4, 128);
+  const size_t vec = align_up(static_cast<size_t>(B) * H * nq_pad * 4, 128);
+  return acc + 2 * vec;
+}
+
+int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
+  if (a.head_dim != kHeadDim) return LCBI_ERR_UNSUPPORTED;
+  if (a.B <= 0 || a.H <= 0 || a.Nq <= 0 || a.Nk <= 0) return LCBI_ERR_BAD_ARG;
+  const int64_t* all_strides[] = {a.q_strides, a.k_strides, a.v_strides, a.o_strides,
+                                  a.do_strides, a.dq_strides, a.dk_strides, a.dv_strides};
+  for (const int64_t* s : all_strides)
+    for (int i = 0; i < 3; ++i)
+      if (s[i] % 8 != 0) return LCBI_ERR_BAD_ARG;
+  const void* ptrs[] = {a.q, a.k, a.v, a.o, a.d_o, a.dq, a.dk, a.dv};
+  for (const void* ptr : ptrs)
+    if (reinterpret_cast<uintptr_t>(ptr) & 15) return LCBI_ERR_BAD_ARG;
+  if (a.workspace_bytes < dense_attn_bwd_workspace_bytes(a.B, a.H, a.Nq, a.head_dim) ||
+      (reinterpret_cast<uintptr_t>(a.workspace) & 127))
+    return LCBI_ERR_WORKSPACE;
+
+  const int nq_pad = static_cast<int>(align_up(static_cast<size_t>(a.Nq), kTile));
+  const size_t acc_bytes = align_up(static_cast<size_t>(a.B) * a.Nq * a.H * kHeadDim * 4, 128);
+  const size_t vec_bytes = align_up(static_cast<size_t>(a.B) * a.H * nq_pad * 4, 128);
+  float* dq_acc = reinterpret_cast<float*>(a.workspace);
+  float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes);
+  float* dsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes + vec_bytes);
+
+  CUtensorMap tq, tk, tv, tdo, tacc, tdk, tdv;
+  if (make_bf16_map(&tq, a.q, a.B, a.H, a.Nq, a.q_strides) || make_bf16_map(&tk, a.k, a.B, a.H, a.Nk, a.k_strides) ||
+      make_bf16_map(&tv, a.v, a.B, a.H, a.Nk, a.v_strides) || make_bf16_map(&tdo, a.d_o, a.B, a.H, a.Nq, a.do_strides) ||
+      make_f32_acc_map(&tacc, dq_acc, a.B, a.H, a.Nq))
+    return LCBI_ERR_TENSOR_MAP;
+  if (a.accumulate_dkv) {
+    if (make_f32_acc_map(&tdk, a.dk, a.B, a.H, a.Nk) || make_f32_acc_map(&tdv, a.dv, a.B, a.H, a.Nk))
+      return LCBI_ERR_TENSOR_MAP;
+  } else {
+    if (make_bf16_map(&tdk, a.dk, a.B, a.H, a.Nk, a.dk_strides) || make_bf16_map(&tdv, a.dv, a.B, a.H, a.Nk, a.dv_strides))
+      return LCBI_ERR_TENSOR_MAP;
+  }
+
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, acc_bytes, stream);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  {
+    const int64_t warps = static_cast<int64_t>(a.B) * a.H * nq_pad;
+    const int threads = 256;
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    bwd_prep_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a.o), reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.lse, lse2, dsum,
+        a.B, a.H, a.Nq, nq_pad, a.o_strides[0], a.o_strides[1], a.o_strides[2], a.do_strides[0], a.do_strides[1],
+        a.do_strides[2]);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+
+  static bool attr_set = false;
+  const int smem_bytes = static_cast<int>(sizeof(BwdSmem)) + 1024;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(dense_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  BwdParams p;
+  p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.Nq_pad = nq_pad;
+  p.scale = a.scale;
+  p.scale_log2 = a.scale * kLog2e;
+  p.lse2 = lse2;
+  p.dsum = dsum;
+  p.accumulate_dkv = a.accumulate_dkv;
+  dim3 grid((a.Nk + kTile - 1) / kTile, a.H, a.B);
+  dense_attn_bwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, tdo, tacc, tdk, tdv, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
+
+  {
+    const int64_t total = static_cast<int64_t>(a.B) * a.Nq * a.H * (kHeadDim / 8);
+    const int threads = 256;
+    bwd_finish_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+        dq_acc, reinterpret_cast<__nv_bfloat16*>(a.dq), a.B, a.H, a.Nq, a.dq_strides[0], a.dq_strides[1],
+        a.dq_strides[2], a.scale);
+    e = cudaGetLastError();
+  }
+  return set_cuda_error(e);
+}
+
+}  // namespace lcbi

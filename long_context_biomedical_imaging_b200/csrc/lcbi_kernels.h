@@ -1,0 +1,39 @@
+// Internal launch interface shared by the kernel translation units and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/lcbi_b200.h"
+
+namespace lcbi {
+
+// records the CUDA error text for lcbi_last_error(); returns LCBI_OK or LCBI_ERR_CUDA
+int set_cuda_error(cudaError_t e);
+void set_error_text(const char* msg);
+
+struct DenseAttnArgs {
+  const void* q; const void* k; const void* v;   // bf16, (B, N, H, d) strided views, d contiguous
+  void* o;                                       // bf16, (B, Nq, H, d) strided view
+  float* lse;                                    // fp32 (B, H, Nq), natural log of the row sums
+  int B, H, Nq, Nk, head_dim;
+  int64_t q_strides[3], k_strides[3], v_strides[3], o_strides[3];  // (batch, row, head) in elements
+  float scale;
+};
+int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream);
+
+struct DenseAttnBwdArgs {
+  const void* q; const void* k; const void* v; const void* o; const void* d_o;  // bf16
+  const float* lse;                                                             // (B, H, Nq)
+  void* dq; void* dk; void* dv;                                                 // bf16 outputs
+  void* workspace; size_t workspace_bytes;
+  int B, H, Nq, Nk, head_dim;
+  int64_t q_strides[3], k_strides[3], v_strides[3], o_strides[3], do_strides[3];
+  int64_t dq_strides[3], dk_strides[3], dv_strides[3];
+  float scale;
+  int accumulate_dkv;   // 0: write bf16 dk/dv; 1: dk/dv are fp32 (B,Nk,H,d) contiguous accumulators (+=)
+};
+size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
+int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream);
+
+}  // namespace lcbi

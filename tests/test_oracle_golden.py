@@ -1,0 +1,105 @@
+"""CPU: the oracle restatement (oracle/) against the golden fixtures generated from the UNMODIFIED reference
+(oracle/make_golden.py). Bit-exact for the integer index maps; fp32 tolerance 1e-5 max-rel for floating point
+(same fp32 arithmetic, different summation order)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_stored, load_golden, max_rel
+from oracle import attention_oracle as ao
+from oracle import window_maps as wm
+
+FP32_TOL = 2e-5
+
+
+def test_window_maps_bit_exact():
+    g = load_golden("window_maps.npz")
+    for case in g["cases"]:
+        grid = tuple(int(x) for x in g[f"{case}/grid"])
+        window = tuple(int(x) for x in g[f"{case}/window"])
+        shift = tuple(int(x) for x in g[f"{case}/shift"])
+        win, sh = wm.resolve_window(grid, window, shift)
+        assert win == tuple(int(x) for x in g[f"{case}/win_used"])
+        assert sh == tuple(int(x) for x in g[f"{case}/shift_used"])
+        check_stored(g, f"{case}/gather_map", wm.gather_map(grid, window, shift))
+        check_stored(g, f"{case}/mask", wm.shift_mask(grid, window, shift))
+
+
+def test_rel_pos_index_bit_exact():
+    g = load_golden("window_maps.npz")
+    for key in [k for k in g.files if k.startswith("relidx/") and k.endswith("/shape")]:
+        window = tuple(int(x) for x in key.split("/")[1].split("x"))
+        check_stored(g, "relidx/" + key.split("/")[1], wm.rel_pos_index(window))
+
+
+def test_region_ids_match_mask_semantics():
+    # mask == 0 exactly where region ids agree, for a shifted + padded case
+    grid, window, shift = (10, 9), (7, 7), (3, 3)
+    ids = wm.region_ids(grid, window, shift)
+    mask = wm.shift_mask(grid, window, shift)
+    assert np.array_equal(mask == 0, ids[:, None, :] == ids[:, :, None])
+    assert set(np.unique(mask)) <= {0.0, -100.0}
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_sablock(case):
+    g = load_golden("sablock.npz")
+    t = {k: torch.from_numpy(g[f"{case}/{k}"]) for k in ["x", "w_qkv", "w_out", "b_out", "y", "dout", "dx", "dw_qkv",
+                                                        "dw_out", "db_out"]}
+    x, w_qkv, w_out, b_out = [t[k].clone().requires_grad_(True) for k in ["x", "w_qkv", "w_out", "b_out"]]
+    y = ao.sablock(x, w_qkv, w_out, b_out, int(g[f"{case}/heads"]))
+    assert max_rel(y.detach(), t["y"]) < FP32_TOL
+    grads = torch.autograd.grad(y, [x, w_qkv, w_out, b_out], t["dout"])
+    for got, key in zip(grads, ["dx", "dw_qkv", "dw_out", "db_out"]):
+        assert max_rel(got, t[key]) < FP32_TOL, key
+
+
+def _swin_case(g, name):
+    meta = [int(v) for v in g[f"{name}/meta"]]
+    B, C, H, K = meta[:4]
+    grid = tuple(meta[4:4 + K])
+    window = tuple(meta[4 + K:4 + 2 * K])
+    shift = tuple(meta[4 + 2 * K:4 + 3 * K])
+    return B, C, H, grid, window, shift
+
+
+def test_swin_part1_all_cases():
+    g = load_golden("swin_part1.npz")
+    for name in g["cases"]:
+        B, C, H, grid, window, shift = _swin_case(g, name)
+        keys = ["x", "norm_w", "norm_b", "w_qkv", "b_qkv", "table", "w_proj", "b_proj"]
+        leaves = [torch.from_numpy(g[f"{name}/{k}"]).clone().requires_grad_(True) for k in keys]
+        x, nw, nb, wq, bq, tb, wp, bp = leaves
+        y = ao.swin_part1(x, window, shift, wq, bq, tb, wp, bp, H, norm_w=nw, norm_b=nb)
+        assert max_rel(y.detach(), g[f"{name}/y"]) < FP32_TOL, name
+        grads = torch.autograd.grad(y, leaves, torch.from_numpy(g[f"{name}/dout"]))
+        for got, key in zip(grads, ["dx", "dnorm_w", "dnorm_b", "dw_qkv", "db_qkv", "dtable", "dw_proj", "db_proj"]):
+            assert max_rel(got, g[f"{name}/{key}"]) < 5e-5, (name, key)
+
+
+def test_patch_embed():
+    g = load_golden("patch_embed.npz")
+    for name in ["vit2d", "vit3d", "vit2d_p2"]:
+        x, w, b, pos = [torch.from_numpy(g[f"{name}/{k}"]).clone().requires_grad_(True) for k in ["x", "w", "b", "pos"]]
+        y = ao.patch_embed_vit(x, w, b, pos)
+        assert max_rel(y.detach(), g[f"{name}/y"]) < FP32_TOL
+        grads = torch.autograd.grad(y, [x, w, b, pos], torch.from_numpy(g[f"{name}/dout"]))
+        for got, key in zip(grads, ["dx", "dw", "db", "dpos"]):
+            assert max_rel(got, g[f"{name}/{key}"]) < FP32_TOL, (name, key)
+    for name in ["swin2d", "swin3d"]:
+        x, w, b = [torch.from_numpy(g[f"{name}/{k}"]).clone().requires_grad_(True) for k in ["x", "w", "b"]]
+        y = ao.patch_embed_swin(x, w, b)
+        assert max_rel(y.detach(), g[f"{name}/y"]) < FP32_TOL
+        grads = torch.autograd.grad(y, [x, w, b], torch.from_numpy(g[f"{name}/dout"]))
+        for got, key in zip(grads, ["dx", "dw", "db"]):
+            assert max_rel(got, g[f"{name}/{key}"]) < FP32_TOL, (name, key)
+
+
+def test_dense_attention_rows_matches_full():
+    torch.manual_seed(0)
+    q, k, v = torch.randn(3, 300, 64).unbind(0)
+    full = ao.dense_attention(q[None, None], k[None, None], v[None, None], 0.125)[0, 0]
+    rows, lse = ao.dense_attention_rows(q[[0, 17, 299]], k, v, 0.125, chunk=64)
+    assert max_rel(rows.float(), full[[0, 17, 299]]) < 1e-5
+    ref_lse = torch.logsumexp((q[[0, 17, 299]] @ k.T) * 0.125, -1)
+    assert max_rel(lse.float(), ref_lse) < 1e-5
