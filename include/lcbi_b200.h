@@ -63,6 +63,26 @@ int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void*
                         const int64_t* dk_strides, const int64_t* dv_strides, float scale, int accumulate_dkv,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Patch-embedding projection. Replaces MONAI 1.3.0 PatchEmbeddingBlock (proj_type="conv") as called at
+ * model/models/backbone_vit.py:351-361,383 and MONAI PatchEmbed as called at backbone_swin.py:800-806,885:
+ * a strided convolution with kernel == stride == patch, i.e. an implicit GEMM over non-overlapping patches.
+ *   img : (B, Cin, D, H, W) contiguous, fp32 or bf16 (D = 1 for 2-D)
+ *   w   : (N, Cin*Pd*Ph*Pw) fp32 — the conv weight (hidden, Cin, *patch) viewed flat;  bias: (N) fp32
+ *   pos : (Gd*Gh*Gw, N) fp32 position embedding added per token, or NULL (Swin)
+ *   out : (B, Gd*Gh*Gw, N) token-major fp32 or bf16 (tokens in raster order of the patch grid)
+ *   img_dims/patch/grid: int[3] in (D,H,W) order. grid = floor(img/patch) reproduces PatchEmbeddingBlock,
+ *   grid = ceil(img/patch) reproduces PatchEmbed's trailing zero padding.
+ * The backward writes dw (N,K), dbias (N), and optionally dpos (Gd*Gh*Gw, N) and dimg (B,Cin,D,H,W), all fp32;
+ * pass NULL for dpos / dimg / dbias to skip them.
+ * ---------------------------------------------------------------------------------------------- */
+int lcbi_patch_embed_fwd(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
+                         void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
+                         const int* grid, int N, void* stream);
+int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
+                         float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
+                         const int* patch, const int* grid, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

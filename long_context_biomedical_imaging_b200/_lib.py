@@ -16,6 +16,7 @@ _lib = None
 
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_vp = ctypes.c_void_p
+c_i32p = ctypes.POINTER(ctypes.c_int32)
 
 # name -> (restype, argtypes); must list every symbol include/lcbi_b200.h declares
 SIGNATURES = {
@@ -27,6 +28,10 @@ SIGNATURES = {
     "lcbi_dense_attn_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "lcbi_dense_attn_bwd": (ctypes.c_int, [c_vp] * 9 + [ctypes.c_int] * 5 + [c_i64p] * 8 +
                             [ctypes.c_float, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "lcbi_patch_embed_fwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
+    "lcbi_patch_embed_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
+                                            ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
 }
 
 
@@ -57,6 +62,10 @@ def check(rc: int, what: str):
         if rc in (-1, -2):
             raise ValueError(f"{what} failed ({rc}): {msg}")
         raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def int3(vals):
+    return (ctypes.c_int32 * 3)(*[int(v) for v in vals])
 
 
 def strides3(*vals):

@@ -1,0 +1,135 @@
+"""Building blocks the reference takes from MONAI 1.3.0 (not vendored in the reference; requirements.txt:5),
+re-implemented with identical parameter names / shapes so state_dicts interchange.
+
+  PatchEmbeddingBlock  (reference call site backbone_vit.py:351-361,383)   keys: patch_embeddings.{weight,bias},
+                                                                                 position_embeddings
+  PatchEmbed           (reference call site backbone_swin.py:800-806,885)  keys: proj.{weight,bias}
+  MLPBlock             (backbone_vit.py:249, backbone_swin.py:433)         keys: linear1.*, linear2.*
+
+The two patch-embedding modules run the fused CUDA kernel (ops.patch_embed); MLPBlock is plain torch
+(adjacent component).
+"""
+from __future__ import annotations
+
+from collections.abc import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def ensure_tuple_rep(x, n):
+    if isinstance(x, (list, tuple)):
+        if len(x) == n:
+            return tuple(int(v) for v in x)
+        if len(x) == 1:
+            return tuple(int(x[0]) for _ in range(n))
+        raise ValueError(f"sequence must have length {n}, got {len(x)}")
+    return tuple(int(x) for _ in range(n))
+
+
+class MLPBlock(nn.Module):
+    """linear1 -> GELU -> linear2 (all dropouts are 0 on the reference's reachable paths)."""
+
+    def __init__(self, hidden_size: int, mlp_dim: int, dropout_rate: float = 0.0, act: str = "GELU",
+                 dropout_mode: str = "vit") -> None:
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if act != "GELU":
+            raise ValueError("only GELU is used by the reference encoders")
+        self.linear1 = nn.Linear(hidden_size, mlp_dim)
+        self.linear2 = nn.Linear(mlp_dim, hidden_size)
+        self.fn = nn.GELU()
+        self.drop1 = nn.Dropout(dropout_rate)
+        self.drop2 = nn.Dropout(dropout_rate)
+
+    def forward(self, x):
+        return self.drop2(self.linear2(self.drop1(self.fn(self.linear1(x)))))
+
+
+def _conv_like_init_(weight, bias):
+    """torch.nn.ConvNd default initialisation (what MONAI's conv projection gets)."""
+    nn.init.kaiming_uniform_(weight, a=5 ** 0.5)
+    fan_in = weight[0].numel()
+    bound = 1 / fan_in ** 0.5 if fan_in > 0 else 0
+    nn.init.uniform_(bias, -bound, bound)
+
+
+class _ConvParams(nn.Module):
+    """Holds `weight (out, in, *kernel)` / `bias (out)` under the same names a torch ConvNd would."""
+
+    def __init__(self, in_channels, out_channels, kernel):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, *kernel))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.kernel_size = tuple(kernel)
+        self.stride = tuple(kernel)
+        _conv_like_init_(self.weight, self.bias)
+
+
+class PatchEmbeddingBlock(nn.Module):
+    """ViT patch embedding: strided-conv projection + learnable position embedding -> (B, N, hidden) fp32."""
+
+    def __init__(self, in_channels: int, img_size: Sequence[int] | int, patch_size: Sequence[int] | int,
+                 hidden_size: int, num_heads: int, proj_type: str = "conv", pos_embed_type: str = "learnable",
+                 dropout_rate: float = 0.0, spatial_dims: int = 3) -> None:
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if hidden_size % num_heads != 0:
+            raise ValueError("hidden size should be divisible by num_heads.")
+        if proj_type != "conv":
+            raise ValueError("only proj_type='conv' is used by the reference encoder (backbone_vit.py:288,357)")
+        img_size = ensure_tuple_rep(img_size, spatial_dims)
+        patch_size = ensure_tuple_rep(patch_size, spatial_dims)
+        for m, p in zip(img_size, patch_size):
+            if m < p:
+                raise ValueError("patch_size should be smaller than img_size.")
+        self.img_size, self.patch_size = img_size, patch_size
+        self.grid = tuple(m // p for m, p in zip(img_size, patch_size))
+        self.n_patches = 1
+        for g in self.grid:
+            self.n_patches *= g
+        self.patch_embeddings = _ConvParams(in_channels, hidden_size, patch_size)
+        self.position_embeddings = nn.Parameter(torch.zeros(1, self.n_patches, hidden_size))
+        self.dropout = nn.Dropout(dropout_rate)
+        if pos_embed_type == "learnable":
+            nn.init.trunc_normal_(self.position_embeddings, mean=0.0, std=0.02, a=-2.0, b=2.0)
+        elif pos_embed_type != "none":
+            raise ValueError(f"pos_embed_type {pos_embed_type} not supported")
+
+    def forward(self, x):
+        grid = tuple(s // p for s, p in zip(x.shape[2:], self.patch_size))   # conv floors
+        n = 1
+        for g in grid:
+            n *= g
+        if n != self.n_patches:
+            raise RuntimeError(f"input yields {n} patches, position embedding has {self.n_patches}")
+        return ops.patch_embed(x, self.patch_embeddings.weight, self.patch_embeddings.bias, self.position_embeddings,
+                               grid, torch.float32)
+
+
+class PatchEmbed(nn.Module):
+    """Swin patch embedding: trailing zero-pad to a patch multiple + strided-conv projection.
+
+    forward returns the CHANNEL-LAST token grid (B, *grid, C); the Swin encoder exposes channel-first views of
+    it exactly where the reference returns channel-first tensors."""
+
+    def __init__(self, patch_size: Sequence[int] | int = 2, in_chans: int = 1, embed_dim: int = 48, norm_layer=None,
+                 spatial_dims: int = 3) -> None:
+        super().__init__()
+        if spatial_dims not in (2, 3):
+            raise ValueError("spatial dimension should be 2 or 3.")
+        if norm_layer is not None:
+            raise NotImplementedError("patch_norm is always False in the reference (backbone_swin.py:760,804)")
+        self.patch_size = ensure_tuple_rep(patch_size, spatial_dims)
+        self.embed_dim = embed_dim
+        self.proj = _ConvParams(in_chans, embed_dim, self.patch_size)
+        self.norm = None
+
+    def forward(self, x, out_dtype=torch.float32):
+        grid = tuple(-(-s // p) for s, p in zip(x.shape[2:], self.patch_size))   # ceil: trailing zero pad
+        tokens = ops.patch_embed(x, self.proj.weight, self.proj.bias, None, grid, out_dtype)
+        return tokens.view(x.shape[0], *grid, self.embed_dim)

@@ -93,4 +93,26 @@ int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void*
   return rc;
 }
 
+int lcbi_patch_embed_fwd(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
+                         void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
+                         const int* grid, int N, void* stream) {
+  if (!img || !w || !bias || !out || !img_dims || !patch || !grid)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_patch_embed_fwd: null pointer argument");
+  int rc = patch_embed_fwd_launch(img, img_is_bf16, w, bias, pos, out, out_is_bf16, B, Cin, img_dims, patch, grid, N,
+                                  static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_patch_embed_fwd: non-positive size");
+  return rc;
+}
+
+int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
+                         float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
+                         const int* patch, const int* grid, int N, void* stream) {
+  if (!img || !w || !dout || !dw || !img_dims || !patch || !grid)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_patch_embed_bwd: null pointer argument");
+  int rc = patch_embed_bwd_launch(img, img_is_bf16, w, dout, dout_is_bf16, dw, dbias, dpos, dimg, B, Cin, img_dims,
+                                  patch, grid, N, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_patch_embed_bwd: non-positive size");
+  return rc;
+}
+
 }  // extern "C"

@@ -118,3 +118,70 @@ def dense_attention_qkv(qkv, num_heads, scale=None):
     x = qkv if qkv.dtype == torch.bfloat16 else qkv.to(torch.bfloat16)
     o = _DenseAttentionQKV.apply(x.view(B, N, 3, num_heads, d), float(scale))
     return o if o.dtype == qkv.dtype else o.to(qkv.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# patch embedding
+# --------------------------------------------------------------------------------------------------
+def _triple(vals):
+    vals = [int(v) for v in vals]
+    return [1] * (3 - len(vals)) + vals
+
+
+class _PatchEmbed(torch.autograd.Function):
+    """img (B,Cin,*sp) -> tokens (B, Np, N). weight: conv weight (N,Cin,*patch); pos: (1,Np,N) or None."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias, pos, grid, out_bf16):
+        _require_cuda(img, weight, bias)
+        img_c = img.contiguous()
+        if img_c.dtype not in (torch.float32, torch.bfloat16):
+            img_c = img_c.float()
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous()
+        p = pos.detach().float().contiguous() if pos is not None else None
+        B, Cin = img_c.shape[:2]
+        N = w.shape[0]
+        img_dims, patch, grid3 = _triple(img_c.shape[2:]), _triple(w.shape[2:]), _triple(grid)
+        Np = grid3[0] * grid3[1] * grid3[2]
+        out = torch.empty((B, Np, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=img.device)
+        lib = _lib.load()
+        rc = lib.lcbi_patch_embed_fwd(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(b),
+                                      _p(p) if p is not None else None, _p(out), int(out_bf16), B, Cin,
+                                      _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _stream())
+        _lib.check(rc, "lcbi_patch_embed_fwd")
+        ctx.save_for_backward(img_c, w)
+        ctx.geom = (img_dims, patch, grid3, B, Cin, N)
+        ctx.meta = (weight.shape, weight.dtype, bias.dtype, None if pos is None else (pos.shape, pos.dtype),
+                    img.shape, img.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img_c, w = ctx.saved_tensors
+        img_dims, patch, grid3, B, Cin, N = ctx.geom
+        w_shape, w_dtype, b_dtype, pos_meta, img_shape, img_dtype = ctx.meta
+        dout = dout.contiguous()
+        if dout.dtype not in (torch.float32, torch.bfloat16):
+            dout = dout.float()
+        dev = dout.device
+        Np = grid3[0] * grid3[1] * grid3[2]
+        dw = torch.empty((N, w.numel() // N), dtype=torch.float32, device=dev)
+        db = torch.empty((N,), dtype=torch.float32, device=dev)
+        dpos = torch.empty((Np, N), dtype=torch.float32, device=dev) if (pos_meta and ctx.needs_input_grad[3]) else None
+        dimg = torch.empty(img_c.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        lib = _lib.load()
+        rc = lib.lcbi_patch_embed_bwd(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(dout),
+                                      int(dout.dtype == torch.bfloat16), _p(dw), _p(db),
+                                      _p(dpos) if dpos is not None else None, _p(dimg) if dimg is not None else None,
+                                      B, Cin, _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _stream())
+        _lib.check(rc, "lcbi_patch_embed_bwd")
+        return (dimg.to(img_dtype).view(img_shape) if dimg is not None else None, dw.view(w_shape).to(w_dtype),
+                db.to(b_dtype), dpos.view(pos_meta[0]).to(pos_meta[1]) if dpos is not None else None, None, None)
+
+
+def patch_embed(img, weight, bias, pos, grid, out_dtype=torch.float32):
+    """Fused strided-conv patch projection (+bias, +position embedding): (B,Cin,*sp) -> (B, prod(grid), N)."""
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("patch_embed output dtype must be float32 or bfloat16")
+    return _PatchEmbed.apply(img, weight, bias, pos, tuple(int(g) for g in grid), out_dtype == torch.bfloat16)
