@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: attention fwd+bwd tokens/s (BASELINE.json metric) on the 3-D ViT-B configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload = "cfg3"): BASELINE.json configs[2] — ViT-B 3D encoder, 96^3 volume, patch 8 ->
+1728 tokens, 12 heads x 64, bf16 — the configuration the metric's tensor-pipe target is quoted on. One "step" =
+one global-attention layer (the hot path: fused QK^T -> softmax -> PV forward and its backward) over a batch of
+16 synthetic volumes per GPU = 27,648 layer-tokens per GPU per step. N > 1 shards the batch (independent
+samples, no data-path collective): scaling "weak".
+
+Printed JSON (one line, rank 0): value = whole-job tokens/s with inputs resident in HBM; e2e = same metric with the
+step's inputs (qkv, dO) copied from pinned host memory and a result scalar read back inside the timed region;
+roofline = the backward launch group (the dominant kernel) against the measured bf16 tensor peak;
+cpu_baseline = the oracle's CPU restatement of the same attention timed on this box's host cores.
+
+`--impl reference` times the reference algorithm's CPU path (oracle port: the reference is pure PyTorch and its
+tree does not exist on the GPU box) on the same config, with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "attention fwd+bwd tokens/s"
+UNIT = "tokens/s"
+CFG3 = dict(B=16, N=1728, H=12, d=64, C=768)
+N_BUFFERS = 4  # rotating input sets (each step's qkv+dO = 170 MB > the 126 MB L2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"bf16_tflops": float(d["bf16_tflops"]), "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", 0)),
+                "hbm_gbs": float(d["hbm_gbs"]), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_cpu_tokens_per_s(seconds_budget=12.0, sample_b=1):
+    """fwd+bwd of the oracle's dense attention (reference algorithm, backbone_vit.py:191-201) on host cores."""
+    from oracle import attention_oracle as ao
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    N, H, d = CFG3["N"], CFG3["H"], CFG3["d"]
+    g = torch.Generator().manual_seed(0)
+    q, k, v = [torch.randn(sample_b, H, N, d, generator=g, requires_grad=True) for _ in range(3)]
+    d_o = torch.randn(sample_b, H, N, d, generator=g)
+
+    def step():
+        o = ao.dense_attention(q, k, v, d ** -0.5)
+        torch.autograd.grad(o, [q, k, v], d_o)
+
+    step()  # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < 30):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return sample_b * N / best, threads, f"oracle attention core fp32, B={sample_b} x {H} heads x {N} tokens, best of {len(times)}", times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each "step" = one fwd+bwd of a 1-sample slice of the cfg3 batch on all host threads
+    from oracle import attention_oracle as ao
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    N, H, d = CFG3["N"], CFG3["H"], CFG3["d"]
+    g = torch.Generator().manual_seed(0)
+    q, k, v = [torch.randn(1, H, N, d, generator=g, requires_grad=True) for _ in range(3)]
+    d_o = torch.randn(1, H, N, d, generator=g)
+
+    def step():
+        o = ao.dense_attention(q, k, v, d ** -0.5)
+        torch.autograd.grad(o, [q, k, v], d_o)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * N / dt
+    sample = f"1 of the {CFG3['B']} volumes per step (fp32, {H} heads x {N} tokens), oracle port of backbone_vit.py:191-201"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3: ViT-B 3D 96^3 patch 8, 1728 tokens, 12 heads x 64 (CPU sample: 1 volume/step)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG3["B"], help="volumes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 10
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_reference_arm(args)
+        return
+    args.steps = args.steps if args.steps is not None else 300
+    args.warmup = max(3, args.warmup if args.warmup is not None else 20)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from long_context_biomedical_imaging_b200 import ops
+
+    B, N, H, d, C = args.batch, CFG3["N"], CFG3["H"], CFG3["d"], CFG3["C"]
+    scale = d ** -0.5
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(rank)
+    qkvs = [torch.randn(B, N, 3, H, d, device=dev).to(torch.bfloat16) for _ in range(N_BUFFERS)]
+    d_os = [torch.randn(B, N, H, d, device=dev).to(torch.bfloat16) for _ in range(N_BUFFERS)]
+    o = torch.empty(B, N, H, d, device=dev, dtype=torch.bfloat16)
+    dqkv = torch.empty_like(qkvs[0])
+
+    def step(i, ev=None):
+        qkv, d_o = qkvs[i % N_BUFFERS], d_os[i % N_BUFFERS]
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        _, lse = ops.dense_attn_fwd(q, k, v, scale, out=o)
+        if ev is not None:
+            ev[0].record()
+        ops.dense_attn_bwd(q, k, v, o, d_o, lse, scale, dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2])
+        if ev is not None:
+            ev[1].record()
+        return lse
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    bwd_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i, bwd_events[i])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in bwd_events)
+
+    # ---------------- timed region 2 (e2e): pinned host inputs -> H2D -> fwd+bwd -> scalar D2H, every step
+    host_qkv = [t.cpu().pin_memory() for t in qkvs[:2]]
+    host_do = [t.cpu().pin_memory() for t in d_os[:2]]
+    dev_qkv, dev_do = torch.empty_like(qkvs[0]), torch.empty_like(d_os[0])
+    result_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    e2e_steps = max(10, args.steps // 10)
+
+    def e2e_step(i):
+        dev_qkv.copy_(host_qkv[i % 2], non_blocking=True)
+        dev_do.copy_(host_do[i % 2], non_blocking=True)
+        q, k, v = dev_qkv[:, :, 0], dev_qkv[:, :, 1], dev_qkv[:, :, 2]
+        _, lse = ops.dense_attn_fwd(q, k, v, scale, out=o)
+        ops.dense_attn_bwd(q, k, v, o, dev_do, lse, scale, dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2])
+        result_host.copy_(dqkv.view(-1)[:1].float(), non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    if dist is not None:
+        t = torch.tensor([ms_total, e2e_ms, bwd_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms, bwd_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peaks = measured_peaks()
+        tokens_per_step = world * B * N
+        value = tokens_per_step * args.steps / (ms_total * 1e-3)
+        e2e_value = tokens_per_step * e2e_steps / (e2e_ms * 1e-3)
+        alg_flops_step = 12.0 * B * N * N * C          # per GPU, fwd 4 + bwd 8
+        bwd_flops = 8.0 * B * N * N * C
+        bwd_tflops = bwd_flops / (bwd_ms * 1e-3) / 1e12
+        step_tflops = alg_flops_step / (ms_total / args.steps * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "cfg3: ViT-B 3D encoder attention layer, 96^3 volume, patch 8 -> 1728 tokens, "
+                                   "12 heads x 64, fwd+bwd", "volumes_per_gpu": B, "tokens_per_step": tokens_per_step,
+                       "parallelism": f"batch-sharded x{world} (no data-path collective)",
+                       "l2": f"inputs rotate over {N_BUFFERS} buffer sets of 170 MB (> 126 MB L2)"},
+            "tflops_algorithmic_per_gpu": step_tflops,
+            "tensor_frac_of_measured_peak": step_tflops / peaks["bf16_tflops"],
+            "roofline": {"bound": "tensor", "kernel": "dense_attn_bwd launch group (prep + bwd_main + finish)",
+                         "achieved": bwd_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": bwd_tflops / peaks["bf16_tflops"], "traffic": None,
+                         "peak_source": peaks["source"] + " (burst)", "peak_sustained": peaks["bf16_tflops_sustained"],
+                         "algorithmic_flops_per_launch": bwd_flops, "avg_launch_ms": bwd_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(dev_qkv.numel() * 2 + dev_do.numel() * 2), "d2h_bytes_per_step": 4},
+            "gpu_launches": 4 * args.steps,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            v, cores, sample, _ = oracle_cpu_tokens_per_s()
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

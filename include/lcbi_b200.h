@@ -83,6 +83,41 @@ int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const
                          float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
                          const int* patch, const int* grid, int N, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Swin (shifted-)window attention. Replaces, as ONE gather -> attention -> scatter kernel, the body of
+ * SwinTransformerBlock.forward_part1 between the qkv and proj Linear layers
+ * (model/models/backbone_swin.py:441-485: F.pad, torch.roll, window_partition, window_reverse, torch.roll, crop)
+ * and the attention core of WindowAttention.forward (:339-357: q*scale, q k^T, + relative_position_bias_table[
+ * relative_position_index[:n,:n]], + compute_mask(...) (:591-628), softmax, @ v).
+ *   ndim 2|3; grid/window/shift: int[ndim] token grid and the CONSTRUCTOR window / shift sizes (the per-axis
+ *   clamp of get_window_size, :200-224, is applied inside).
+ *   qkv      : bf16 (B, T, 3, H, d) — output of the qkv Linear on the UN-padded, un-shifted token grid
+ *   qkv_bias : fp32 (3*H*d) — q/k/v of the zero-pad tokens (the reference pads after norm1), or NULL
+ *   table    : fp32 (prod(2*window-1), H) relative_position_bias_table
+ *   out      : bf16 (B, T, H*d) attention output at the source token position (input of the proj Linear)
+ *   lse2     : fp32 (B, T, H) log2-domain log-sum-exp per real token (consumed by the backward)
+ * head_dim must be 16 or 32 (all Swin presets: backbone_swin.py:56-94); prod(clamped window) <= 512.
+ *
+ * Backward: d_out bf16 (B,T,H*d), o = forward output; writes dqkv bf16 (B,T,3,H,d); ACCUMULATES (+=, caller
+ * zero-initialises) dbias_pad fp32 (3*H*d) = gradient reaching qkv.bias through pad tokens, and dtable fp32
+ * (same shape as table). dsum: fp32 (B,T,H) scratch.
+ * ---------------------------------------------------------------------------------------------- */
+int lcbi_win_attn_fwd(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                      float scale, const void* qkv, const float* qkv_bias, const float* table, void* out, float* lse2,
+                      void* stream);
+int lcbi_win_attn_bwd(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                      float scale, const void* qkv, const float* qkv_bias, const float* table, const void* o,
+                      const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad, float* dtable,
+                      void* stream);
+
+/* Index maps as tensors, for bit-exactness checks against window_partition(roll(pad(.))) (:135-165,:459-468),
+ * compute_mask (:591-628) and relative_position_index (:256-308):
+ *   gather (nW*n) int32: source token of each window slot, -1 for pad tokens; region (nW*n) int32: shift-mask
+ *   region id (mask[w,i,j] = region[w,i] == region[w,j] ? 0 : -100); relidx (n*n) int32: the [:n,:n] slice.
+ * Any of the three may be NULL. n_out / nw_out (host ints) receive tokens per window / windows per image. */
+int lcbi_window_maps(int ndim, const int* grid, const int* window, const int* shift, int* gather, int* region,
+                     int* relidx, int* n_out, int* nw_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

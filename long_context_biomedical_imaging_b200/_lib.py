@@ -32,6 +32,11 @@ SIGNATURES = {
                                             ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
     "lcbi_patch_embed_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
                                             ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
+    "lcbi_win_attn_fwd": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "lcbi_win_attn_bwd": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_float] + [c_vp] * 11),
+    "lcbi_window_maps": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_i32p, c_i32p, c_vp]),
 }
 
 
@@ -62,6 +67,11 @@ def check(rc: int, what: str):
         if rc in (-1, -2):
             raise ValueError(f"{what} failed ({rc}): {msg}")
         raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def int_array(vals):
+    vals = [int(v) for v in vals]
+    return (ctypes.c_int32 * len(vals))(*vals)
 
 
 def int3(vals):

@@ -115,4 +115,47 @@ int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const
   return rc;
 }
 
+static int win_status(int rc, const char* who) {
+  static thread_local char buf[256];
+  const char* why = nullptr;
+  if (rc == LCBI_ERR_UNSUPPORTED) why = "head_dim must be 16 or 32 and the window must hold <= 512 tokens";
+  if (rc == LCBI_ERR_BAD_ARG) why = "bad ndim / grid / window / shift / batch / heads";
+  if (!why) return rc;
+  std::snprintf(buf, sizeof(buf), "%s: %s", who, why);
+  return fail(rc, buf);
+}
+
+int lcbi_win_attn_fwd(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                      float scale, const void* qkv, const float* qkv_bias, const float* table, void* out, float* lse2,
+                      void* stream) {
+  if (!grid || !window || !shift || !qkv || !table || !out || !lse2)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_win_attn_fwd: null pointer argument");
+  WinAttnArgs a{};
+  a.ndim = ndim; a.grid = grid; a.window = window; a.shift = shift;
+  a.B = B; a.H = H; a.head_dim = head_dim; a.scale = scale;
+  a.qkv = qkv; a.qkv_bias = qkv_bias; a.table = table; a.out = out; a.lse2 = lse2;
+  return win_status(win_attn_fwd_launch(a, static_cast<cudaStream_t>(stream)), "lcbi_win_attn_fwd");
+}
+
+int lcbi_win_attn_bwd(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                      float scale, const void* qkv, const float* qkv_bias, const float* table, const void* o,
+                      const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad, float* dtable,
+                      void* stream) {
+  if (!grid || !window || !shift || !qkv || !table || !o || !lse2 || !d_out || !dsum || !dqkv)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_win_attn_bwd: null pointer argument");
+  WinAttnArgs a{};
+  a.ndim = ndim; a.grid = grid; a.window = window; a.shift = shift;
+  a.B = B; a.H = H; a.head_dim = head_dim; a.scale = scale;
+  a.qkv = qkv; a.qkv_bias = qkv_bias; a.table = table; a.lse2 = const_cast<float*>(lse2);
+  a.d_out = d_out; a.dsum = dsum; a.dqkv = dqkv; a.dbias_pad = dbias_pad; a.dtable = dtable;
+  return win_status(win_attn_bwd_launch(a, o, static_cast<cudaStream_t>(stream)), "lcbi_win_attn_bwd");
+}
+
+int lcbi_window_maps(int ndim, const int* grid, const int* window, const int* shift, int* gather, int* region,
+                     int* relidx, int* n_out, int* nw_out, void* stream) {
+  if (!grid || !window || !shift) return fail(LCBI_ERR_BAD_ARG, "lcbi_window_maps: null pointer argument");
+  return win_status(window_maps_launch(ndim, grid, window, shift, gather, region, relidx, n_out, nw_out,
+                                       static_cast<cudaStream_t>(stream)), "lcbi_window_maps");
+}
+
 }  // extern "C"

@@ -44,4 +44,28 @@ int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, con
                            float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
                            const int* patch, const int* grid, int N, cudaStream_t stream);
 
+// Swin window attention (window_attn.cu)
+struct WinAttnArgs {
+  int ndim;                       // 2 or 3
+  const int* grid;                // token grid, ndim entries
+  const int* window;              // constructor window size
+  const int* shift;               // constructor shift size (all zeros for W-MSA blocks)
+  int B, H, head_dim;
+  float scale;
+  const void* qkv;                // bf16 (B, T, 3, H, d)
+  const float* qkv_bias;          // fp32 (3*H*d) or null
+  const float* table;             // fp32 (prod(2*window-1), H)
+  void* out;                      // bf16 (B, T, H*d)
+  float* lse2;                    // fp32 (B, T, H)
+  const void* d_out;              // bf16 (B, T, H*d)            [bwd]
+  float* dsum;                    // fp32 (B, T, H) scratch      [bwd]
+  void* dqkv;                     // bf16 (B, T, 3, H, d)        [bwd]
+  float* dbias_pad;               // fp32 (3*H*d), +=            [bwd]
+  float* dtable;                  // fp32 like table, +=         [bwd]
+};
+int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream);
+int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream);
+int window_maps_launch(int ndim, const int* grid, const int* window, const int* shift, int* gather, int* region,
+                       int* relidx, int* n_out, int* nw_out, cudaStream_t stream);
+
 }  // namespace lcbi

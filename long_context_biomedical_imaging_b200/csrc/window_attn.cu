@@ -1,0 +1,823 @@
+// Swin (shifted-)window multi-head attention for sm_100a: fused gather -> QK^T + relative-position bias +
+// shift mask -> softmax -> PV -> scatter, forward and backward.
+//
+// Replaces, without any of their copies, the reference's
+//   SwinTransformerBlock.forward_part1   /root/reference/model/models/backbone_swin.py:435-487
+//     (F.pad -> torch.roll -> window_partition -> attention -> window_reverse -> torch.roll -> crop)
+//   WindowAttention.forward attention core   :339-357   (q*scale, q k^T, + bias[index], + mask, softmax, @ v)
+//   compute_mask   :591-628   (never materialised: region ids are evaluated per window slot)
+// The per-token qkv / proj Linear layers stay outside (they commute with the gather/scatter): the kernels
+// read q/k/v straight out of the (B, T, 3, H, d) qkv Linear output through the closed-form window map, take
+// `qkv.bias` as the q/k/v rows of the zero-pad tokens (the reference pads AFTER norm1, so a pad token's qkv is
+// exactly the bias, :437-445 + :339), and write the attention output back to (B, T, C) at the source token.
+//
+// These kernels use warp-level mma.sync tiles: head_dim is 16 or 32 and windows hold 49..512 tokens, so the
+// work per (window, head) is far below a tcgen05 tile; the bound is HBM traffic / exp throughput, not the
+// tensor pipe ("window attention roofline").
+#include "lcbi_kernels.h"
+#include "window_common.cuh"
+
+namespace lcbi {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kKeyChunk = 64;
+
+struct WinParams {
+  WinGeom g;
+  int B, H, C;
+  float scale_log2;             // head_dim^-0.5 * log2(e)
+  const __nv_bfloat16* qkv;     // (B, T, 3, H, D)
+  const float* qkv_bias;        // (3*C) or nullptr
+  const float* table;           // (tab_rows, H)
+  __nv_bfloat16* out;           // (B, T, C)                      [fwd]
+  float* lse2;                  // (B, T, H) log2-domain logsumexp [fwd out / bwd in]
+  // backward
+  const __nv_bfloat16* d_out;   // (B, T, C)
+  const float* dsum;            // (B, T, H) rowsum(dO o O)
+  __nv_bfloat16* dqkv;          // (B, T, 3, H, D)
+  float* dbias_pad;             // (3*C) fp32, += gradient reaching qkv.bias through the pad tokens
+  float* dtable;                // (tab_rows, H) fp32, +=
+  int win_splits;               // dq kernel: number of window subsets
+};
+
+template <int D>
+struct Tile {
+  static constexpr int kStride = D * 2 + 16;   // bytes per smem row: +16 keeps ldmatrix conflict-free
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// -------------------------------------------------------------------------------------------------
+// per-CTA window metadata in shared memory
+// -------------------------------------------------------------------------------------------------
+struct WinMeta {
+  int* tok;        // [n_pad] token index, -1 pad token, -2 slot beyond the window
+  int* reg;        // [n_pad] region id
+  int* row_term;   // [n_pad]
+  int* col_term;   // [n_pad]
+};
+
+__device__ __forceinline__ void fill_meta(const WinGeom& g, int w, int n_pad, WinMeta m, int tid, int nthreads) {
+  for (int s = tid; s < n_pad; s += nthreads) {
+    int tok = -2, region = -1, rt = g.tab_rows - 1, ct = 0;   // rt - ct stays a valid table row for dead slots
+    if (s < g.n) {
+      slot_lookup(g, w, s, tok, region);
+      relpos_terms(g, s, rt, ct);
+    }
+    m.tok[s] = tok;
+    m.reg[s] = region;
+    m.row_term[s] = rt;
+    m.col_term[s] = ct;
+  }
+}
+
+// loads rows [row_begin, row_end) of one of q/k/v (or dO when sel == 3) for (batch b, head h) into a smem tile
+template <int D>
+__device__ __forceinline__ void load_rows(uint8_t* tile, const WinParams& p, const int* tok, int b, int h, int sel,
+                                          int row_begin, int row_end, int tid, int nthreads) {
+  constexpr int kChunks = D / 8;   // 16-byte chunks per row
+  const int total = (row_end - row_begin) * kChunks;
+  for (int e = tid; e < total; e += nthreads) {
+    const int r = row_begin + e / kChunks, c = e % kChunks;
+    const int t = tok[r];
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0) {
+      const __nv_bfloat16* src;
+      if (sel < 3)
+        src = p.qkv + ((static_cast<int64_t>(b) * p.g.T + t) * 3 + sel) * p.C + h * D + c * 8;
+      else
+        src = p.d_out + (static_cast<int64_t>(b) * p.g.T + t) * p.C + h * D + c * 8;
+      val = *reinterpret_cast<const uint4*>(src);
+    } else if (t == -1 && sel < 3 && p.qkv_bias != nullptr) {
+      const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+      val.x = pack2_bf16(bsrc[0], bsrc[1]);
+      val.y = pack2_bf16(bsrc[2], bsrc[3]);
+      val.z = pack2_bf16(bsrc[4], bsrc[5]);
+      val.w = pack2_bf16(bsrc[6], bsrc[7]);
+    }
+    *reinterpret_cast<uint4*>(tile + r * Tile<D>::kStride + c * 16) = val;
+  }
+}
+
+// =================================================================================================
+// forward: CTA = (window, head), 4 warps, each warp owns 16-row query tiles
+// =================================================================================================
+template <int D>
+__global__ void __launch_bounds__(128)
+win_attn_fwd_kernel(const WinParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const WinGeom& g = p.g;
+  const int n = g.n, n_pad = round_up(n, kKeyChunk);
+  constexpr int kStride = Tile<D>::kStride;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + n_pad * kStride;
+  uint8_t* sV = sK + n_pad * kStride;
+  float* tab = reinterpret_cast<float*>(sV + n_pad * kStride);
+  WinMeta meta;
+  meta.tok = reinterpret_cast<int*>(tab + round_up(g.tab_rows, 4));
+  meta.reg = meta.tok + n_pad;
+  meta.row_term = meta.reg + n_pad;
+  meta.col_term = meta.row_term + n_pad;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wg = blockIdx.x, h = blockIdx.y;
+  const int b = wg / g.nW, w = wg % g.nW;
+
+  fill_meta(g, w, n_pad, meta, tid, 128);
+  for (int t = tid; t < g.tab_rows; t += 128) tab[t] = p.table[t * p.H + h] * kLog2e;
+  __syncthreads();
+  load_rows<D>(sQ, p, meta.tok, b, h, 0, 0, n_pad, tid, 128);
+  load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, 128);
+  load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, 128);
+  __syncthreads();
+
+  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  const int gq = lane >> 2, qq = lane & 3;
+  const float mask_log2 = -100.0f * kLog2e;
+  const int n_qt = (n + 15) / 16;
+
+  for (int qt = warp; qt < n_qt; qt += 4) {
+    const int row0 = qt * 16;
+    uint32_t aq[D / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) load_a_frag<kStride>(aq[kk], q_base, row0, kk * 16, lane);
+    const int i0 = row0 + gq, i1 = i0 + 8;
+    const int rt0 = meta.row_term[i0], rt1 = meta.row_term[i1];
+    const int rg0 = meta.reg[i0], rg1 = meta.reg[i1];
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float oacc[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+
+    for (int kc = 0; kc < n_pad; kc += kKeyChunk) {
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t b0, b1;
+          load_b_frag_nt<kStride>(b0, b1, k_base, kc + nt * 8, kk * 16, lane);
+          mma_bf16_16816(s[nt], aq[kk], b0, b1);
+        }
+      }
+      // logits (log2 domain) = s*scale*log2e + bias*log2e + mask*log2e ; columns beyond the window -> -inf
+      float cmax0 = -INFINITY, cmax1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = kc + nt * 8 + qq * 2 + e;
+          float v0 = -INFINITY, v1 = -INFINITY;
+          if (j < n) {
+            const int ct = meta.col_term[j], rj = meta.reg[j];
+            v0 = fmaf(s[nt][e], p.scale_log2, tab[rt0 - ct]) + (rg0 != rj ? mask_log2 : 0.f);
+            v1 = fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - ct]) + (rg1 != rj ? mask_log2 : 0.f);
+          }
+          s[nt][e] = v0;
+          s[nt][2 + e] = v1;
+          cmax0 = fmaxf(cmax0, v0);
+          cmax1 = fmaxf(cmax1, v1);
+        }
+      }
+      cmax0 = fmaxf(cmax0, __shfl_xor_sync(0xffffffffu, cmax0, 1));
+      cmax0 = fmaxf(cmax0, __shfl_xor_sync(0xffffffffu, cmax0, 2));
+      cmax1 = fmaxf(cmax1, __shfl_xor_sync(0xffffffffu, cmax1, 1));
+      cmax1 = fmaxf(cmax1, __shfl_xor_sync(0xffffffffu, cmax1, 2));
+      const float mn0 = fmaxf(m0, cmax0), mn1 = fmaxf(m1, cmax1);   // finite: every chunk has >= 1 valid column
+      const float a0 = ex2f(m0 - mn0), a1 = ex2f(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      l0 *= a0; l1 *= a1;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        oacc[i][0] *= a0; oacc[i][1] *= a0; oacc[i][2] *= a1; oacc[i][3] *= a1;
+      }
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = ex2f(s[nt][0] - m0); s[nt][1] = ex2f(s[nt][1] - m0);
+        s[nt][2] = ex2f(s[nt][2] - m1); s[nt][3] = ex2f(s[nt][3] - m1);
+        rs0 += s[nt][0] + s[nt][1];
+        rs1 += s[nt][2] + s[nt][3];
+      }
+      l0 += rs0; l1 += rs1;
+      // O += P V
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {   // 16 keys per step
+        uint32_t ap[4];
+        ap[0] = pack2_bf16(s[2 * kb][0], s[2 * kb][1]);
+        ap[1] = pack2_bf16(s[2 * kb][2], s[2 * kb][3]);
+        ap[2] = pack2_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+        ap[3] = pack2_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) {
+          uint32_t b0, b1;
+          load_b_frag_t<kStride>(b0, b1, v_base, kc + kb * 16, nd * 8, lane);
+          mma_bf16_16816(oacc[nd], ap, b0, b1);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    // stage the 16 x D output tile in this warp's (already consumed) Q rows, then 16-byte scatter stores
+    __syncwarp();
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) {
+      *reinterpret_cast<uint32_t*>(sQ + i0 * kStride + (nd * 8 + qq * 2) * 2) =
+          pack2_bf16(oacc[nd][0] * inv0, oacc[nd][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sQ + i1 * kStride + (nd * 8 + qq * 2) * 2) =
+          pack2_bf16(oacc[nd][2] * inv1, oacc[nd][3] * inv1);
+    }
+    const int t0 = meta.tok[i0], t1 = meta.tok[i1];
+    if (qq == 0) {
+      if (t0 >= 0) p.lse2[(static_cast<int64_t>(b) * g.T + t0) * p.H + h] = m0 + log2f(l0);
+      if (t1 >= 0) p.lse2[(static_cast<int64_t>(b) * g.T + t1) * p.H + h] = m1 + log2f(l1);
+    }
+    __syncwarp();
+    constexpr int kChunks = D / 8;
+    for (int e = lane; e < 16 * kChunks; e += 32) {
+      const int r = row0 + e / kChunks, c = e % kChunks;
+      const int t = meta.tok[r];
+      if (t >= 0)
+        *reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * g.T + t) * p.C + h * D + c * 8) =
+            *reinterpret_cast<const uint4*>(sQ + r * kStride + c * 16);
+    }
+    __syncwarp();
+  }
+}
+
+size_t fwd_smem_bytes(const WinGeom& g, int D) {
+  const int n_pad = round_up(g.n, kKeyChunk);
+  return static_cast<size_t>(3) * n_pad * (D * 2 + 16) + static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 + static_cast<size_t>(n_pad) * 16;
+}
+
+// =================================================================================================
+// backward prep: dsum[b,t,h] = sum_d dO*O (one warp handles 32/(D/8)... simple: one thread per (b,t,h))
+// =================================================================================================
+template <int D>
+__global__ void win_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                    float* __restrict__ dsum, int64_t total, int H, int C) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int h = static_cast<int>(idx % H);
+  const int64_t bt = idx / H;
+  const uint4* po = reinterpret_cast<const uint4*>(o + bt * C + h * D);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + bt * C + h * D);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c) {
+    const uint4 a = po[c], bq = pd[c];
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bq);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __bfloat1622float2(a2[i]), y = __bfloat1622float2(b2[i]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
+  }
+  dsum[idx] = acc;
+}
+
+// per-row backward scalars in smem: lse2 (+inf for pad/out-of-window rows => P = 0) and dsum
+__device__ __forceinline__ void load_row_scalars(const WinParams& p, const int* tok, int b, int h, int row_begin,
+                                                 int row_end, float* s_lse, float* s_dsum, int tid, int nthreads) {
+  for (int r = row_begin + tid; r < row_end; r += nthreads) {
+    const int t = tok[r];
+    float l = INFINITY, d = 0.f;
+    if (t >= 0) {
+      const int64_t idx = (static_cast<int64_t>(b) * p.g.T + t) * p.H + h;
+      l = p.lse2[idx];
+      d = p.dsum[idx];
+    }
+    s_lse[r] = l;
+    s_dsum[r] = d;
+  }
+}
+
+// =================================================================================================
+// backward dK/dV: CTA = (window, head), 4 warps, each warp owns 16-row KEY tiles and sweeps the queries
+//   S^T = K Q^T, P^T = exp2(.), dP^T = V dO^T, dS^T = P^T o (dP^T - D[q]); dV += P^T dO; dK += dS^T Q
+// =================================================================================================
+template <int D>
+__global__ void __launch_bounds__(128)
+win_attn_bwd_dkdv_kernel(const WinParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const WinGeom& g = p.g;
+  const int n = g.n, n_pad = round_up(n, kKeyChunk);
+  constexpr int kStride = Tile<D>::kStride;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + n_pad * kStride;
+  uint8_t* sV = sK + n_pad * kStride;
+  uint8_t* sDO = sV + n_pad * kStride;
+  float* tab = reinterpret_cast<float*>(sDO + n_pad * kStride);
+  float* s_lse = tab + round_up(g.tab_rows, 4);
+  float* s_dsum = s_lse + n_pad;
+  WinMeta meta;
+  meta.tok = reinterpret_cast<int*>(s_dsum + n_pad);
+  meta.reg = meta.tok + n_pad;
+  meta.row_term = meta.reg + n_pad;
+  meta.col_term = meta.row_term + n_pad;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wg = blockIdx.x, h = blockIdx.y;
+  const int b = wg / g.nW, w = wg % g.nW;
+
+  fill_meta(g, w, n_pad, meta, tid, 128);
+  for (int t = tid; t < g.tab_rows; t += 128) tab[t] = p.table[t * p.H + h] * kLog2e;
+  __syncthreads();
+  load_rows<D>(sQ, p, meta.tok, b, h, 0, 0, n_pad, tid, 128);
+  load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, 128);
+  load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, 128);
+  load_rows<D>(sDO, p, meta.tok, b, h, 3, 0, n_pad, tid, 128);
+  load_row_scalars(p, meta.tok, b, h, 0, n_pad, s_lse, s_dsum, tid, 128);
+  __syncthreads();
+
+  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  const uint32_t do_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDO));
+  const int gq = lane >> 2, qq = lane & 3;
+  const float mask_log2 = -100.0f * kLog2e;
+  const int n_kt = (n + 15) / 16;
+  const float scale = p.scale_log2 / kLog2e;
+  float pad_dk[D / 8][2], pad_dv[D / 8][2];   // gradient reaching qkv.bias through pad-token keys/values
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) pad_dk[i][0] = pad_dk[i][1] = pad_dv[i][0] = pad_dv[i][1] = 0.f;
+
+  for (int kt = warp; kt < n_kt; kt += 4) {
+    const int key0 = kt * 16;
+    uint32_t ak[D / 16][4], av[D / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      load_a_frag<kStride>(ak[kk], k_base, key0, kk * 16, lane);
+      load_a_frag<kStride>(av[kk], v_base, key0, kk * 16, lane);
+    }
+    const int j0 = key0 + gq, j1 = j0 + 8;           // key rows held by this thread
+    const int ct0 = meta.col_term[j0], ct1 = meta.col_term[j1];
+    const int rg0 = meta.reg[j0], rg1 = meta.reg[j1];
+    const bool kv0 = j0 < n, kv1 = j1 < n;
+    float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    for (int qc = 0; qc < n_pad; qc += 32) {   // 32 queries per step (4 n-tiles)
+      float st[4][4], dp[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t b0, b1;
+          load_b_frag_nt<kStride>(b0, b1, q_base, qc + nt * 8, kk * 16, lane);
+          mma_bf16_16816(st[nt], ak[kk], b0, b1);
+          load_b_frag_nt<kStride>(b0, b1, do_base, qc + nt * 8, kk * 16, lane);
+          mma_bf16_16816(dp[nt], av[kk], b0, b1);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = qc + nt * 8 + qq * 2 + e;     // query index (column of the transposed tile)
+          const float lse = s_lse[i], dsm = s_dsum[i];
+          const int rt = meta.row_term[i], ri = meta.reg[i];
+          float p0 = 0.f, p1 = 0.f;
+          if (kv0) p0 = ex2f(fmaf(st[nt][e], p.scale_log2, tab[rt - ct0]) + (ri != rg0 ? mask_log2 : 0.f) - lse);
+          if (kv1) p1 = ex2f(fmaf(st[nt][2 + e], p.scale_log2, tab[rt - ct1]) + (ri != rg1 ? mask_log2 : 0.f) - lse);
+          st[nt][e] = p0;
+          st[nt][2 + e] = p1;
+          dp[nt][e] = p0 * (dp[nt][e] - dsm);
+          dp[nt][2 + e] = p1 * (dp[nt][2 + e] - dsm);
+        }
+      }
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {   // 16 queries per MMA k-step
+        uint32_t ap[4], ads[4];
+        ap[0] = pack2_bf16(st[2 * kb][0], st[2 * kb][1]);
+        ap[1] = pack2_bf16(st[2 * kb][2], st[2 * kb][3]);
+        ap[2] = pack2_bf16(st[2 * kb + 1][0], st[2 * kb + 1][1]);
+        ap[3] = pack2_bf16(st[2 * kb + 1][2], st[2 * kb + 1][3]);
+        ads[0] = pack2_bf16(dp[2 * kb][0], dp[2 * kb][1]);
+        ads[1] = pack2_bf16(dp[2 * kb][2], dp[2 * kb][3]);
+        ads[2] = pack2_bf16(dp[2 * kb + 1][0], dp[2 * kb + 1][1]);
+        ads[3] = pack2_bf16(dp[2 * kb + 1][2], dp[2 * kb + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) {
+          uint32_t b0, b1;
+          load_b_frag_t<kStride>(b0, b1, do_base, qc + kb * 16, nd * 8, lane);
+          mma_bf16_16816(dv[nd], ap, b0, b1);
+          load_b_frag_t<kStride>(b0, b1, q_base, qc + kb * 16, nd * 8, lane);
+          mma_bf16_16816(dk[nd], ads, b0, b1);
+        }
+      }
+    }
+    // write dK (scaled) / dV rows of real tokens; pad-token rows feed the qkv.bias gradient
+    const int t0 = meta.tok[j0], t1 = meta.tok[j1];
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) {
+      const int col = h * D + nd * 8 + qq * 2;
+      if (t0 >= 0) {
+        const int64_t base = (static_cast<int64_t>(b) * g.T + t0) * 3 * p.C;
+        *reinterpret_cast<uint32_t*>(p.dqkv + base + p.C + col) = pack2_bf16(dk[nd][0] * scale, dk[nd][1] * scale);
+        *reinterpret_cast<uint32_t*>(p.dqkv + base + 2 * p.C + col) = pack2_bf16(dv[nd][0], dv[nd][1]);
+      } else if (t0 == -1) {
+        pad_dk[nd][0] += dk[nd][0] * scale; pad_dk[nd][1] += dk[nd][1] * scale;
+        pad_dv[nd][0] += dv[nd][0]; pad_dv[nd][1] += dv[nd][1];
+      }
+      if (t1 >= 0) {
+        const int64_t base = (static_cast<int64_t>(b) * g.T + t1) * 3 * p.C;
+        *reinterpret_cast<uint32_t*>(p.dqkv + base + p.C + col) = pack2_bf16(dk[nd][2] * scale, dk[nd][3] * scale);
+        *reinterpret_cast<uint32_t*>(p.dqkv + base + 2 * p.C + col) = pack2_bf16(dv[nd][2], dv[nd][3]);
+      } else if (t1 == -1) {
+        pad_dk[nd][0] += dk[nd][2] * scale; pad_dk[nd][1] += dk[nd][3] * scale;
+        pad_dv[nd][0] += dv[nd][2]; pad_dv[nd][1] += dv[nd][3];
+      }
+    }
+  }
+  if (p.dbias_pad != nullptr && g.n * g.nW != g.T) {   // the window grid contains pad tokens
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = pad_dk[nd][e], c = pad_dv[nd][e];
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, off);
+          c += __shfl_xor_sync(0xffffffffu, c, off);
+        }
+        if (gq == 0) {
+          const int col = h * D + nd * 8 + qq * 2 + e;
+          if (a != 0.f) atomicAdd(p.dbias_pad + p.C + col, a);
+          if (c != 0.f) atomicAdd(p.dbias_pad + 2 * p.C + col, c);
+        }
+      }
+    }
+  }
+}
+
+size_t dkdv_smem_bytes(const WinGeom& g, int D) {
+  const int n_pad = round_up(g.n, kKeyChunk);
+  return static_cast<size_t>(4) * n_pad * (D * 2 + 16) + static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 +
+         static_cast<size_t>(n_pad) * 8 + static_cast<size_t>(n_pad) * 16;
+}
+
+// =================================================================================================
+// backward dQ + d(relative_position_bias_table):
+//   CTA = (head, 32-row query slab, window subset); warp (qt, ks) = 16-row query tile x 128-key split.
+//   Loops over its windows keeping dBias[32 x n] for the slab in registers; per window dQ = dS K.
+// =================================================================================================
+constexpr int kSlabRows = 32;
+constexpr int kKeySplit = 128;
+
+template <int D>
+__global__ void __launch_bounds__(256)
+win_attn_bwd_dq_kernel(const WinParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const WinGeom& g = p.g;
+  const int n = g.n, n_pad = round_up(n, kKeySplit);
+  constexpr int kStride = Tile<D>::kStride;
+  const int n_ks = n_pad / kKeySplit;
+  const int nthreads = blockDim.x;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + n_pad * kStride;
+  uint8_t* sQ = sV + n_pad * kStride;            // [32 rows]
+  uint8_t* sDO = sQ + kSlabRows * kStride;       // [32 rows]
+  float* tab = reinterpret_cast<float*>(sDO + kSlabRows * kStride);
+  float* s_lse = tab + round_up(g.tab_rows, 4);               // [32]
+  float* s_dsum = s_lse + kSlabRows;             // [32]
+  float* s_dq = s_dsum + kSlabRows;              // [n_ks][32][D] fp32 partial dQ
+  WinMeta meta;
+  meta.tok = reinterpret_cast<int*>(s_dq + n_ks * kSlabRows * D);
+  meta.reg = meta.tok + n_pad;
+  meta.row_term = meta.reg + n_pad;
+  meta.col_term = meta.row_term + n_pad;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qt = warp & 1, ks = warp >> 1;
+  const int slab = blockIdx.x, h = blockIdx.y, split = blockIdx.z;
+  const int row_base = slab * kSlabRows;          // first window slot of this slab
+  const int gq = lane >> 2, qq = lane & 3;
+  const float mask_log2 = -100.0f * kLog2e;
+  const float scale = p.scale_log2 / kLog2e;
+
+  for (int t = tid; t < g.tab_rows; t += nthreads) tab[t] = p.table[t * p.H + h] * kLog2e;
+
+  float dbias[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dbias[i][0] = dbias[i][1] = dbias[i][2] = dbias[i][3] = 0.f;
+
+  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+  const uint32_t do_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDO));
+  const int total_windows = p.B * g.nW;
+
+  for (int wg = split; wg < total_windows; wg += p.win_splits) {
+    const int b = wg / g.nW, w = wg % g.nW;
+    __syncthreads();                              // previous window fully consumed
+    fill_meta(g, w, n_pad, meta, tid, nthreads);
+    __syncthreads();
+    load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, nthreads);
+    load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, nthreads);
+    // slab rows: Q and dO (rows beyond n_pad cannot occur: row_base + 32 <= round_up(n, 32) <= n_pad)
+    {
+      constexpr int kChunks = D / 8;
+      for (int e = tid; e < kSlabRows * kChunks * 2; e += nthreads) {
+        const int which = e / (kSlabRows * kChunks);   // 0: Q, 1: dO
+        const int r = (e / kChunks) % kSlabRows, c = e % kChunks;
+        const int t = meta.tok[row_base + r];
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0) {
+          const __nv_bfloat16* src = which == 0
+              ? p.qkv + ((static_cast<int64_t>(b) * g.T + t) * 3) * p.C + h * D + c * 8
+              : p.d_out + (static_cast<int64_t>(b) * g.T + t) * p.C + h * D + c * 8;
+          val = *reinterpret_cast<const uint4*>(src);
+        }
+        *reinterpret_cast<uint4*>((which == 0 ? sQ : sDO) + r * kStride + c * 16) = val;
+      }
+      for (int r = tid; r < kSlabRows; r += nthreads) {
+        const int t = meta.tok[row_base + r];
+        float l = INFINITY, dsv = 0.f;
+        if (t >= 0) {
+          const int64_t idx = (static_cast<int64_t>(b) * g.T + t) * p.H + h;
+          l = p.lse2[idx];
+          dsv = p.dsum[idx];
+        }
+        s_lse[r] = l;
+        s_dsum[r] = dsv;
+      }
+    }
+    __syncthreads();
+
+    uint32_t aq[D / 16][4], ado[D / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      load_a_frag<kStride>(aq[kk], q_base, qt * 16, kk * 16, lane);
+      load_a_frag<kStride>(ado[kk], do_base, qt * 16, kk * 16, lane);
+    }
+    const int r0 = qt * 16 + gq, r1 = r0 + 8;                 // rows inside the slab
+    const int i0 = row_base + r0, i1 = row_base + r1;         // window slots
+    const float lse0 = s_lse[r0], lse1 = s_lse[r1], ds0 = s_dsum[r0], ds1 = s_dsum[r1];
+    const int rt0 = meta.row_term[i0], rt1 = meta.row_term[i1];
+    const int rg0 = meta.reg[i0], rg1 = meta.reg[i1];
+    float dq[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {            // 32 keys per step inside this warp's 128-key split
+      const int key0 = ks * kKeySplit + sub * 32;
+      float s[4][4], dp[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t b0, b1;
+          load_b_frag_nt<kStride>(b0, b1, k_base, key0 + nt * 8, kk * 16, lane);
+          mma_bf16_16816(s[nt], aq[kk], b0, b1);
+          load_b_frag_nt<kStride>(b0, b1, v_base, key0 + nt * 8, kk * 16, lane);
+          mma_bf16_16816(dp[nt], ado[kk], b0, b1);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = key0 + nt * 8 + qq * 2 + e;
+          float d0 = 0.f, d1 = 0.f;
+          if (j < n) {
+            const int ct = meta.col_term[j], rj = meta.reg[j];
+            const float p0 = ex2f(fmaf(s[nt][e], p.scale_log2, tab[rt0 - ct]) + (rg0 != rj ? mask_log2 : 0.f) - lse0);
+            const float p1 = ex2f(fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - ct]) + (rg1 != rj ? mask_log2 : 0.f) - lse1);
+            d0 = p0 * (dp[nt][e] - ds0);
+            d1 = p1 * (dp[nt][2 + e] - ds1);
+          }
+          dp[nt][e] = d0;
+          dp[nt][2 + e] = d1;
+          dbias[sub * 4 + nt][e] += d0;
+          dbias[sub * 4 + nt][2 + e] += d1;
+        }
+      }
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        uint32_t ads[4];
+        ads[0] = pack2_bf16(dp[2 * kb][0], dp[2 * kb][1]);
+        ads[1] = pack2_bf16(dp[2 * kb][2], dp[2 * kb][3]);
+        ads[2] = pack2_bf16(dp[2 * kb + 1][0], dp[2 * kb + 1][1]);
+        ads[3] = pack2_bf16(dp[2 * kb + 1][2], dp[2 * kb + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) {
+          uint32_t b0, b1;
+          load_b_frag_t<kStride>(b0, b1, k_base, key0 + kb * 16, nd * 8, lane);
+          mma_bf16_16816(dq[nd], ads, b0, b1);
+        }
+      }
+    }
+    // reduce the key-split partials of dQ through shared memory, then scatter rows of real tokens
+    float* mine = s_dq + (ks * kSlabRows) * D;
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) {
+      *reinterpret_cast<float2*>(mine + r0 * D + nd * 8 + qq * 2) = make_float2(dq[nd][0], dq[nd][1]);
+      *reinterpret_cast<float2*>(mine + r1 * D + nd * 8 + qq * 2) = make_float2(dq[nd][2], dq[nd][3]);
+    }
+    __syncthreads();
+    for (int e = tid; e < kSlabRows * (D / 8); e += nthreads) {
+      const int r = e / (D / 8), c = e % (D / 8);
+      const int t = meta.tok[row_base + r];
+      if (t < 0) continue;
+      float acc[8] = {};
+      for (int s2 = 0; s2 < n_ks; ++s2) {
+        const float4 x = *reinterpret_cast<const float4*>(s_dq + (s2 * kSlabRows + r) * D + c * 8);
+        const float4 y = *reinterpret_cast<const float4*>(s_dq + (s2 * kSlabRows + r) * D + c * 8 + 4);
+        acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+        acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+      }
+      uint4 val;
+      val.x = pack2_bf16(acc[0] * scale, acc[1] * scale);
+      val.y = pack2_bf16(acc[2] * scale, acc[3] * scale);
+      val.z = pack2_bf16(acc[4] * scale, acc[5] * scale);
+      val.w = pack2_bf16(acc[6] * scale, acc[7] * scale);
+      *reinterpret_cast<uint4*>(p.dqkv + (static_cast<int64_t>(b) * g.T + t) * 3 * p.C + h * D + c * 8) = val;
+    }
+  }
+
+  // d(relative_position_bias_table)[idx(i,j), h] += dBias[i, j]   (window-independent index)
+  if (p.dtable != nullptr) {
+    int rt[2], ct_dummy;
+    const int i0 = row_base + qt * 16 + gq, i1 = i0 + 8;
+    relpos_terms(g, i0 < n ? i0 : 0, rt[0], ct_dummy);
+    relpos_terms(g, i1 < n ? i1 : 0, rt[1], ct_dummy);
+#pragma unroll
+    for (int t16 = 0; t16 < 16; ++t16) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = ks * kKeySplit + t16 * 8 + qq * 2 + e;
+        if (j >= n) continue;
+        int rtj, ctj;
+        relpos_terms(g, j, rtj, ctj);
+        if (i0 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt[0] - ctj) * p.H + h, dbias[t16][e]);
+        if (i1 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt[1] - ctj) * p.H + h, dbias[t16][2 + e]);
+      }
+    }
+  }
+}
+
+size_t dq_smem_bytes(const WinGeom& g, int D) {
+  const int n_pad = round_up(g.n, kKeySplit);
+  const int n_ks = n_pad / kKeySplit;
+  return static_cast<size_t>(2) * n_pad * (D * 2 + 16) + static_cast<size_t>(2) * kSlabRows * (D * 2 + 16) +
+         static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 + 2 * kSlabRows * 4 + static_cast<size_t>(n_ks) * kSlabRows * D * 4 +
+         static_cast<size_t>(n_pad) * 16;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) return LCBI_ERR_UNSUPPORTED;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  return LCBI_OK;
+}
+
+int fill_params(WinParams& p, const WinAttnArgs& a) {
+  if (a.B <= 0 || a.H <= 0) return LCBI_ERR_BAD_ARG;
+  if (a.head_dim != 16 && a.head_dim != 32) return LCBI_ERR_UNSUPPORTED;
+  if (fill_win_geom(p.g, a.ndim, a.grid, a.window, a.shift)) return LCBI_ERR_BAD_ARG;
+  if (p.g.n > 512) return LCBI_ERR_UNSUPPORTED;
+  p.B = a.B; p.H = a.H; p.C = a.H * a.head_dim;
+  p.scale_log2 = a.scale * kLog2e;
+  p.qkv = static_cast<const __nv_bfloat16*>(a.qkv);
+  p.qkv_bias = a.qkv_bias;
+  p.table = a.table;
+  p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.lse2 = a.lse2;
+  p.d_out = static_cast<const __nv_bfloat16*>(a.d_out);
+  p.dsum = a.dsum;
+  p.dqkv = static_cast<__nv_bfloat16*>(a.dqkv);
+  p.dbias_pad = a.dbias_pad;
+  p.dtable = a.dtable;
+  p.win_splits = 1;
+  return LCBI_OK;
+}
+
+}  // namespace
+
+int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
+  WinParams p;
+  int rc = fill_params(p, a);
+  if (rc) return rc;
+  const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
+  dim3 grid(p.B * p.g.nW, p.H);
+  if (a.head_dim == 16) {
+    if ((rc = set_smem(win_attn_fwd_kernel<16>, smem))) return rc;
+    win_attn_fwd_kernel<16><<<grid, 128, smem, stream>>>(p);
+  } else {
+    if ((rc = set_smem(win_attn_fwd_kernel<32>, smem))) return rc;
+    win_attn_fwd_kernel<32><<<grid, 128, smem, stream>>>(p);
+  }
+  return set_cuda_error(cudaGetLastError());
+}
+
+int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream) {
+  WinParams p;
+  int rc = fill_params(p, a);
+  if (rc) return rc;
+  const int D = a.head_dim;
+  // 1. dsum = rowsum(dO o O)
+  {
+    const int64_t total = static_cast<int64_t>(p.B) * p.g.T * p.H;
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    if (D == 16)
+      win_bwd_prep_kernel<16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(o), p.d_out, a.dsum, total, p.H, p.C);
+    else
+      win_bwd_prep_kernel<32><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(o), p.d_out, a.dsum, total, p.H, p.C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  // 2. dK, dV (+ pad-token bias gradient)
+  {
+    const size_t smem = dkdv_smem_bytes(p.g, D);
+    dim3 grid(p.B * p.g.nW, p.H);
+    if (D == 16) {
+      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16>, smem))) return rc;
+      win_attn_bwd_dkdv_kernel<16><<<grid, 128, smem, stream>>>(p);
+    } else {
+      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32>, smem))) return rc;
+      win_attn_bwd_dkdv_kernel<32><<<grid, 128, smem, stream>>>(p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  // 3. dQ (+ bias-table gradient)
+  {
+    const size_t smem = dq_smem_bytes(p.g, D);
+    const int n_slabs = (p.g.n + kSlabRows - 1) / kSlabRows;
+    const int n_ks = round_up(p.g.n, kKeySplit) / kKeySplit;
+    const int total_windows = p.B * p.g.nW;
+    int splits = (4 * 148 + n_slabs * p.H - 1) / (n_slabs * p.H);   // aim at ~4 CTAs per SM
+    if (splits > total_windows) splits = total_windows;
+    if (splits < 1) splits = 1;
+    p.win_splits = splits;
+    dim3 grid(n_slabs, p.H, splits);
+    const int threads = 64 * n_ks;
+    if (D == 16) {
+      if ((rc = set_smem(win_attn_bwd_dq_kernel<16>, smem))) return rc;
+      win_attn_bwd_dq_kernel<16><<<grid, threads, smem, stream>>>(p);
+    } else {
+      if ((rc = set_smem(win_attn_bwd_dq_kernel<32>, smem))) return rc;
+      win_attn_bwd_dq_kernel<32><<<grid, threads, smem, stream>>>(p);
+    }
+  }
+  return set_cuda_error(cudaGetLastError());
+}
+
+// -------------------------------------------------------------------------------------------------
+// index maps as tensors (used by the bit-exactness tests): gather map, region ids, relative-position index
+// -------------------------------------------------------------------------------------------------
+namespace {
+__global__ void window_maps_kernel(WinGeom g, int* gather, int* region, int* relidx) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < g.nW * g.n) {
+    int tok, reg;
+    slot_lookup(g, idx / g.n, idx % g.n, tok, reg);
+    if (gather) gather[idx] = tok;
+    if (region) region[idx] = reg;
+  }
+  if (relidx && idx < g.n * g.n) {
+    int rt, ct, rt2, ct2;
+    relpos_terms(g, idx / g.n, rt, ct);
+    relpos_terms(g, idx % g.n, rt2, ct2);
+    relidx[idx] = rt - ct2;
+  }
+}
+}  // namespace
+
+int window_maps_launch(int ndim, const int* grid, const int* window, const int* shift, int* gather, int* region,
+                       int* relidx, int* n_out, int* nw_out, cudaStream_t stream) {
+  WinGeom g;
+  if (fill_win_geom(g, ndim, grid, window, shift)) return LCBI_ERR_BAD_ARG;
+  if (n_out) *n_out = g.n;
+  if (nw_out) *nw_out = g.nW;
+  if (gather || region || relidx) {
+    const int total = max(g.nW * g.n, g.n * g.n);
+    window_maps_kernel<<<(total + 255) / 256, 256, 0, stream>>>(g, gather, region, relidx);
+    return set_cuda_error(cudaGetLastError());
+  }
+  return LCBI_OK;
+}
+
+}  // namespace lcbi

@@ -1,0 +1,135 @@
+// Shared pieces of the Swin window-attention kernels: window geometry (closed-form index maps) and
+// warp-level bf16 MMA fragments.
+//
+// Geometry restates, as integer arithmetic evaluated inside the kernels, what the reference builds with
+// pad / roll / view / permute copies (/root/reference/model/models/backbone_swin.py):
+//   get_window_size :200-224, forward_part1 pad+roll+window_partition :435-468, window_reverse+roll+crop :470-485,
+//   compute_mask :591-628, relative_position_index :256-308 and its [:n,:n] slice :343-345.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace lcbi {
+
+struct WinGeom {
+  int grid[3];      // un-padded token grid (D,H,W); D == 1 for 2-D
+  int win[3];       // window actually used (clamped to the grid)
+  int shift[3];     // shift actually used (0 on clamped axes)
+  int pg[3];        // padded grid (multiple of win)
+  int nwin[3];      // windows per axis
+  int ctor[3];      // constructor window size: defines the relative-position index geometry
+  int n;            // tokens per window
+  int nW;           // windows per image
+  int T;            // tokens per image
+  int tab_rows;     // prod(2*ctor-1)
+};
+
+// host: fills g from (grid, constructor window, constructor shift); ndim 2 or 3 (2-D gets a leading 1)
+inline int fill_win_geom(WinGeom& g, int ndim, const int* grid, const int* window, const int* shift) {
+  if (ndim != 2 && ndim != 3) return -1;
+  const int off = 3 - ndim;
+  g.grid[0] = 1; g.ctor[0] = 1; g.win[0] = 1; g.shift[0] = 0;
+  for (int i = 0; i < ndim; ++i) {
+    if (grid[i] <= 0 || window[i] <= 0 || shift[i] < 0) return -1;
+    g.grid[off + i] = grid[i];
+    g.ctor[off + i] = window[i];
+    if (grid[i] <= window[i]) {        // reference :215-219
+      g.win[off + i] = grid[i];
+      g.shift[off + i] = 0;
+    } else {
+      g.win[off + i] = window[i];
+      g.shift[off + i] = shift[i];
+    }
+  }
+  g.n = 1; g.nW = 1; g.T = 1; g.tab_rows = 1;
+  for (int k = 0; k < 3; ++k) {
+    g.pg[k] = (g.grid[k] + g.win[k] - 1) / g.win[k] * g.win[k];
+    g.nwin[k] = g.pg[k] / g.win[k];
+    g.n *= g.win[k];
+    g.nW *= g.nwin[k];
+    g.T *= g.grid[k];
+    g.tab_rows *= 2 * g.ctor[k] - 1;
+  }
+  return 0;
+}
+
+// token index feeding (window w, slot s), -1 for a zero-pad token; also the shift-mask region id of the slot
+__device__ __forceinline__ void slot_lookup(const WinGeom& g, int w, int s, int& tok, int& region) {
+  const int w2 = w % g.nwin[2], w1 = (w / g.nwin[2]) % g.nwin[1], w0 = w / (g.nwin[2] * g.nwin[1]);
+  const int t2 = s % g.win[2], t1 = (s / g.win[2]) % g.win[1], t0 = s / (g.win[2] * g.win[1]);
+  const int wc[3] = {w0, w1, w2}, tc[3] = {t0, t1, t2};
+  int src[3];
+  bool inside = true;
+  region = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int p = wc[k] * g.win[k] + tc[k];               // position in the rolled (shifted) padded frame
+    int s_k = p + g.shift[k];
+    if (s_k >= g.pg[k]) s_k -= g.pg[k];                    // roll by -shift (reference :461-463)
+    src[k] = s_k;
+    inside = inside && (s_k < g.grid[k]);
+    const int reg = (g.shift[k] == 0) ? 2 : (p < g.pg[k] - g.win[k] ? 0 : (p < g.pg[k] - g.shift[k] ? 1 : 2));
+    region = region * 3 + reg;                              // reference :609-613 counter order
+  }
+  tok = inside ? (src[0] * g.grid[1] + src[1]) * g.grid[2] + src[2] : -1;
+}
+
+// relative-position index = row_term(i) - col_term(j), slots unravelled in the CONSTRUCTOR window
+__device__ __forceinline__ void relpos_terms(const WinGeom& g, int s, int& row_term, int& col_term) {
+  const int c2 = s % g.ctor[2], c1 = (s / g.ctor[2]) % g.ctor[1], c0 = s / (g.ctor[2] * g.ctor[1]);
+  const int st1 = 2 * g.ctor[2] - 1, st0 = st1 * (2 * g.ctor[1] - 1);
+  col_term = c0 * st0 + c1 * st1 + c2;
+  row_term = col_term + (g.ctor[0] - 1) * st0 + (g.ctor[1] - 1) * st1 + (g.ctor[2] - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-level MMA helpers (m16n8k16, bf16 x bf16 -> fp32)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// A fragment (16 rows x 16 k) of a row-major smem tile: row0 = first row, k0 = first column
+template <int STRIDE_BYTES>
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], uint32_t tile_base, int row0, int k0, int lane) {
+  const uint32_t addr = tile_base + (row0 + (lane & 15)) * STRIDE_BYTES + (k0 + (lane >> 4) * 8) * 2;
+  ldsm_x4(a, addr);
+}
+// B fragment for X^T as B (B[k][n] = X[n0+n][k0+k]): 8 rows of X, 16 columns -> (b0, b1)
+template <int STRIDE_BYTES>
+__device__ __forceinline__ void load_b_frag_nt(uint32_t& b0, uint32_t& b1, uint32_t tile_base, int n0, int k0, int lane) {
+  const uint32_t addr = tile_base + (n0 + (lane & 7)) * STRIDE_BYTES + (k0 + ((lane >> 3) & 1) * 8) * 2;
+  ldsm_x2(b0, b1, addr);
+}
+// B fragment for X as B (B[k][n] = X[k0+k][n0+n]): 16 rows of X, 8 columns -> (b0, b1) via transposing load
+template <int STRIDE_BYTES>
+__device__ __forceinline__ void load_b_frag_t(uint32_t& b0, uint32_t& b1, uint32_t tile_base, int k0, int n0, int lane) {
+  const uint32_t addr = tile_base + (k0 + (lane & 15)) * STRIDE_BYTES + n0 * 2;
+  ldsm_x2_trans(b0, b1, addr);
+}
+
+}  // namespace lcbi

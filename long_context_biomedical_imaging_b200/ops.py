@@ -185,3 +185,93 @@ def patch_embed(img, weight, bias, pos, grid, out_dtype=torch.float32):
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("patch_embed output dtype must be float32 or bfloat16")
     return _PatchEmbed.apply(img, weight, bias, pos, tuple(int(g) for g in grid), out_dtype == torch.bfloat16)
+
+
+# --------------------------------------------------------------------------------------------------
+# Swin window attention
+# --------------------------------------------------------------------------------------------------
+class _WindowAttention(torch.autograd.Function):
+    """qkv (B, T, 3, H, d) bf16 on the un-padded token grid -> attention output (B, T, H*d) bf16.
+    qkv_bias (3*H*d) supplies the q/k/v rows of pad tokens; table is relative_position_bias_table."""
+
+    @staticmethod
+    def forward(ctx, qkv, qkv_bias, table, grid, window, shift, scale):
+        _require_cuda(qkv, table)
+        B, T, _, H, d = qkv.shape
+        qkv = qkv.contiguous()
+        bias_f = qkv_bias.detach().float().contiguous() if qkv_bias is not None else None
+        table_f = table.detach().float().contiguous()
+        out = torch.empty((B, T, H * d), dtype=torch.bfloat16, device=qkv.device)
+        lse2 = torch.empty((B, T, H), dtype=torch.float32, device=qkv.device)
+        lib = _lib.load()
+        g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
+        rc = lib.lcbi_win_attn_fwd(len(grid), g, w, s, B, H, d, float(scale), _p(qkv),
+                                   _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2), _stream())
+        _lib.check(rc, "lcbi_win_attn_fwd")
+        ctx.save_for_backward(qkv, bias_f, table_f, out, lse2)
+        ctx.geom = (tuple(grid), tuple(window), tuple(shift), float(scale))
+        ctx.meta = (None if qkv_bias is None else qkv_bias.dtype, table.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, bias_f, table_f, out, lse2 = ctx.saved_tensors
+        grid, window, shift, scale = ctx.geom
+        B, T, _, H, d = qkv.shape
+        d_out = d_out.to(torch.bfloat16).contiguous()
+        dev = qkv.device
+        dqkv = torch.empty_like(qkv)
+        dsum = torch.empty((B, T, H), dtype=torch.float32, device=dev)
+        dbias = torch.zeros((3 * H * d,), dtype=torch.float32, device=dev) if bias_f is not None else None
+        dtable = torch.zeros_like(table_f)
+        lib = _lib.load()
+        g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
+        rc = lib.lcbi_win_attn_bwd(len(grid), g, w, s, B, H, d, scale, _p(qkv), _p(bias_f) if bias_f is not None else None,
+                                   _p(table_f), _p(out), _p(lse2), _p(d_out), _p(dsum), _p(dqkv),
+                                   _p(dbias) if dbias is not None else None, _p(dtable), _stream())
+        _lib.check(rc, "lcbi_win_attn_bwd")
+        bias_dtype, table_dtype = ctx.meta
+        return (dqkv, dbias.to(bias_dtype) if dbias is not None else None, dtable.to(table_dtype), None, None, None, None)
+
+
+def window_attention(qkv, qkv_bias, table, grid, window, shift, num_heads, scale=None):
+    """Fused Swin (shifted-)window attention on the token grid.
+
+    qkv: (B, *grid, 3*C) output of the qkv Linear applied to the un-padded, un-shifted tokens (feature index
+    s*C + h*d + j, reference backbone_swin.py:339); qkv_bias: the Linear's bias (q/k/v of pad tokens) or None;
+    table: relative_position_bias_table; window / shift: CONSTRUCTOR sizes (clamping happens inside).
+    Returns (B, *grid, C) in qkv.dtype — the input of the proj Linear, already back at the source positions."""
+    _require_cuda(qkv)
+    grid = tuple(int(x) for x in grid)
+    B, C3 = qkv.shape[0], qkv.shape[-1]
+    C = C3 // 3
+    d = C // num_heads
+    T = 1
+    for x in grid:
+        T *= x
+    if tuple(qkv.shape[1:-1]) != grid:
+        raise ValueError("qkv must be (B, *grid, 3*C)")
+    if scale is None:
+        scale = d ** -0.5
+    x = qkv if qkv.dtype == torch.bfloat16 else qkv.to(torch.bfloat16)
+    out = _WindowAttention.apply(x.reshape(B, T, 3, num_heads, d), qkv_bias, table, grid,
+                                 tuple(int(v) for v in window), tuple(int(v) for v in shift), float(scale))
+    out = out.view(B, *grid, C)
+    return out if out.dtype == qkv.dtype else out.to(qkv.dtype)
+
+
+def window_maps(grid, window, shift, device="cuda"):
+    """(gather_map (nW,n) int32, region_ids (nW,n) int32, rel_pos_index (n,n) int32) computed by the CUDA code
+    path's own closed forms — for bit-exactness tests against the reference's pad/roll/partition/compute_mask."""
+    lib = _lib.load()
+    g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
+    n, nw = ctypes.c_int32(0), ctypes.c_int32(0)
+    rc = lib.lcbi_window_maps(len(grid), g, w, s, None, None, None, ctypes.byref(n), ctypes.byref(nw), None)
+    _lib.check(rc, "lcbi_window_maps")
+    gather = torch.empty((nw.value, n.value), dtype=torch.int32, device=device)
+    region = torch.empty((nw.value, n.value), dtype=torch.int32, device=device)
+    relidx = torch.empty((n.value, n.value), dtype=torch.int32, device=device)
+    rc = lib.lcbi_window_maps(len(grid), g, w, s, _p(gather), _p(region), _p(relidx), ctypes.byref(n), ctypes.byref(nw),
+                              _stream())
+    _lib.check(rc, "lcbi_window_maps")
+    return gather, region, relidx

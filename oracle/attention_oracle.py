@@ -100,15 +100,16 @@ def swin_part1(x, window_ctor, shift_ctor, w_qkv, b_qkv, table, w_proj, b_proj, 
     grid = tuple(x.shape[1:-1])
     win, sh = wm.resolve_window(grid, window_ctor, shift_ctor)
     n = int(np.prod(win))
-    gmap = torch.from_numpy(wm.gather_map(grid, window_ctor, shift_ctor))  # (nW, n)
+    gmap = torch.from_numpy(wm.gather_map(grid, window_ctor, shift_ctor)).to(x.device)  # (nW, n)
     nW = gmap.shape[0]
     xn = F.layer_norm(x, (C,), norm_w, norm_b) if norm_w is not None else x
     flat = xn.reshape(B, -1, C)
     valid = gmap >= 0
     idx = gmap.clamp(min=0)
     xw = flat[:, idx.reshape(-1)].reshape(B, nW, n, C) * valid[None, :, :, None].to(x.dtype)  # pad rows = 0
-    index_nn = torch.from_numpy(wm.rel_pos_index_used(window_ctor, n))
-    mask = torch.from_numpy(wm.shift_mask(grid, window_ctor, shift_ctor)).to(x.dtype) if any(s > 0 for s in sh) else None
+    index_nn = torch.from_numpy(wm.rel_pos_index_used(window_ctor, n)).to(x.device)
+    mask = (torch.from_numpy(wm.shift_mask(grid, window_ctor, shift_ctor)).to(device=x.device, dtype=x.dtype)
+            if any(s > 0 for s in sh) else None)
     yw = window_attention(xw.reshape(B * nW, n, C), w_qkv, b_qkv, table, index_nn, mask, w_proj, b_proj,
                           num_heads).reshape(B, nW * n, C)
     out = torch.zeros_like(flat)
