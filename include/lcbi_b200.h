@@ -54,6 +54,7 @@ int lcbi_dense_attn_fwd(const void* q, const void* k, const void* v, void* o, fl
  *   d_o, o: (B,Nq,H,d) bf16 views; dq: (B,Nq,H,d), dk/dv: (B,Nk,H,d) bf16 views.
  *   accumulate_dkv != 0: dk/dv are instead fp32 (B,Nk,H,d) CONTIGUOUS buffers that are accumulated into
  *   (ring sequence-parallel steps); their stride arguments are ignored.
+ *   accumulate_dq != 0: likewise dq is an fp32 (B,Nq,H,d) contiguous buffer that is accumulated into.
  *   workspace: at least lcbi_dense_attn_bwd_workspace_bytes() bytes, 128-byte aligned. */
 size_t lcbi_dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
 int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
@@ -61,7 +62,15 @@ int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void*
                         const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
                         const int64_t* o_strides, const int64_t* do_strides, const int64_t* dq_strides,
                         const int64_t* dk_strides, const int64_t* dv_strides, float scale, int accumulate_dkv,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Combine step of ring (sequence-parallel) attention — functionality the reference does not have (it cannot run
+ * global attention beyond a few thousand tokens: the N x N matrix of backbone_vit.py:193 is materialised).
+ * Merges a partial result (o_s bf16 (B,N,H,64) contiguous, lse_s fp32 (B,H,N)) into the running fp32 accumulator
+ * (acc (B,N,H,64), lse_acc (B,H,N)); first != 0 initialises the accumulator instead. If out_bf16 is not NULL the
+ * merged output is also written there as bf16 (B,N,H,64). */
+int lcbi_attn_merge(float* acc, float* lse_acc, const void* o_s, const float* lse_s, void* out_bf16, int B, int N, int H,
+                    int head_dim, int first, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Patch-embedding projection. Replaces MONAI 1.3.0 PatchEmbeddingBlock (proj_type="conv") as called at

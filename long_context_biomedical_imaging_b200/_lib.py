@@ -27,7 +27,9 @@ SIGNATURES = {
                                            c_vp]),
     "lcbi_dense_attn_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "lcbi_dense_attn_bwd": (ctypes.c_int, [c_vp] * 9 + [ctypes.c_int] * 5 + [c_i64p] * 8 +
-                            [ctypes.c_float, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+                            [ctypes.c_float, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "lcbi_attn_merge": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, c_vp]),
     "lcbi_patch_embed_fwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
     "lcbi_patch_embed_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,

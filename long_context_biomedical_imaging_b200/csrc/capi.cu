@@ -67,9 +67,9 @@ int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void*
                         const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
                         const int64_t* o_strides, const int64_t* do_strides, const int64_t* dq_strides,
                         const int64_t* dk_strides, const int64_t* dv_strides, float scale, int accumulate_dkv,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream) {
   if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !workspace || !q_strides || !k_strides ||
-      !v_strides || !o_strides || !do_strides || !dq_strides)
+      !v_strides || !o_strides || !do_strides || (!accumulate_dq && !dq_strides))
     return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_bwd: null pointer argument");
   if (!accumulate_dkv && (!dk_strides || !dv_strides))
     return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_bwd: dk/dv strides required unless accumulate_dkv");
@@ -79,12 +79,15 @@ int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void*
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
   a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.head_dim = head_dim;
   copy3(a.q_strides, q_strides); copy3(a.k_strides, k_strides); copy3(a.v_strides, v_strides);
-  copy3(a.o_strides, o_strides); copy3(a.do_strides, do_strides); copy3(a.dq_strides, dq_strides);
+  copy3(a.o_strides, o_strides); copy3(a.do_strides, do_strides);
+  const int64_t contiguous_q[3] = {static_cast<int64_t>(Nq) * H * head_dim, static_cast<int64_t>(H) * head_dim, head_dim};
+  copy3(a.dq_strides, accumulate_dq ? contiguous_q : dq_strides);
   const int64_t contiguous[3] = {static_cast<int64_t>(Nk) * H * head_dim, static_cast<int64_t>(H) * head_dim, head_dim};
   copy3(a.dk_strides, accumulate_dkv ? contiguous : dk_strides);
   copy3(a.dv_strides, accumulate_dkv ? contiguous : dv_strides);
   a.scale = scale;
   a.accumulate_dkv = accumulate_dkv;
+  a.accumulate_dq = accumulate_dq;
   int rc = dense_attn_bwd_launch(a, static_cast<cudaStream_t>(stream));
   if (rc == LCBI_ERR_UNSUPPORTED) return fail(rc, "lcbi_dense_attn_bwd: only head_dim == 64 is implemented");
   if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_dense_attn_bwd: bad size, or pointer/stride not 16-byte aligned");
@@ -112,6 +115,15 @@ int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const
   int rc = patch_embed_bwd_launch(img, img_is_bf16, w, dout, dout_is_bf16, dw, dbias, dpos, dimg, B, Cin, img_dims,
                                   patch, grid, N, static_cast<cudaStream_t>(stream));
   if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_patch_embed_bwd: non-positive size");
+  return rc;
+}
+
+int lcbi_attn_merge(float* acc, float* lse_acc, const void* o_s, const float* lse_s, void* out_bf16, int B, int N, int H,
+                    int head_dim, int first, void* stream) {
+  if (!acc || !lse_acc || !o_s || !lse_s) return fail(LCBI_ERR_BAD_ARG, "lcbi_attn_merge: null pointer argument");
+  int rc = attn_merge_launch(acc, lse_acc, o_s, lse_s, out_bf16, B, N, H, head_dim, first, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_UNSUPPORTED) return fail(rc, "lcbi_attn_merge: only head_dim == 64 is implemented");
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_attn_merge: non-positive size");
   return rc;
 }
 

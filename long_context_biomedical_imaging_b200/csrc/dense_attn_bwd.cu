@@ -87,42 +87,52 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// prep: D = rowsum(dO o O), lse2 = lse * log2e; one warp per (b, h, row)
+// prep: D = rowsum(dO o O), lse2 = lse * log2e; 8 threads per (b, h, row)
 // ------------------------------------------------------------------------------------------------
 __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                 const float* __restrict__ lse, float* __restrict__ lse2, float* __restrict__ dsum,
                                 int B, int H, int Nq, int Nq_pad, int64_t o_sb, int64_t o_sr, int64_t o_sh,
                                 int64_t do_sb, int64_t do_sr, int64_t do_sh) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  // 8 threads per (b, h, row): each loads 16 bytes of O and dO; rows ordered (b, row, h) so that a warp's four
+  // rows are adjacent heads of one token (contiguous 512 bytes in the usual (B,N,H,d) layout)
+  const int sub = threadIdx.x & 7;
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int64_t total = static_cast<int64_t>(B) * H * Nq_pad;
-  if (warp_global >= total) return;
-  const int row = static_cast<int>(warp_global % Nq_pad);
-  const int h = static_cast<int>((warp_global / Nq_pad) % H);
-  const int b = static_cast<int>(warp_global / (static_cast<int64_t>(Nq_pad) * H));
+  if (r >= total) return;
+  const int h = static_cast<int>(r % H);
+  const int row = static_cast<int>((r / H) % Nq_pad);
+  const int b = static_cast<int>(r / (static_cast<int64_t>(H) * Nq_pad));
+  const int64_t out_idx = (static_cast<int64_t>(b) * H + h) * Nq_pad + row;
   if (row >= Nq) {
-    if (lane == 0) {
-      lse2[warp_global] = INFINITY;   // exp2(x - inf) = 0: padded query columns contribute nothing
-      dsum[warp_global] = 0.f;
+    if (sub == 0) {
+      lse2[out_idx] = INFINITY;   // exp2(x - inf) = 0: padded query columns contribute nothing
+      dsum[out_idx] = 0.f;
     }
     return;
   }
-  const __nv_bfloat162 ov =
-      *reinterpret_cast<const __nv_bfloat162*>(o + b * o_sb + row * o_sr + h * o_sh + lane * 2);
-  const __nv_bfloat162 dv =
-      *reinterpret_cast<const __nv_bfloat162*>(d_o + b * do_sb + row * do_sr + h * do_sh + lane * 2);
-  float acc = __bfloat162float(ov.x) * __bfloat162float(dv.x) + __bfloat162float(ov.y) * __bfloat162float(dv.y);
+  const uint4 ov = *reinterpret_cast<const uint4*>(o + b * o_sb + row * o_sr + h * o_sh + sub * 8);
+  const uint4 dv = *reinterpret_cast<const uint4*>(d_o + b * do_sb + row * do_sr + h * do_sh + sub * 8);
+  const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+  const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+  float acc = 0.f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) {
-    dsum[warp_global] = acc;
-    lse2[warp_global] = lse[(static_cast<int64_t>(b) * H + h) * Nq + row] * kLog2e;
+  for (int i = 0; i < 4; ++i) {
+    const float2 x = __bfloat1622float2(o2[i]), y = __bfloat1622float2(d2[i]);
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0) {
+    dsum[out_idx] = acc;
+    lse2[out_idx] = lse[(static_cast<int64_t>(b) * H + h) * Nq + row] * kLog2e;
   }
 }
 
-// dq = bf16(scale * dq_accum); one thread = 8 consecutive elements of one (b, row, h)
+// dq = bf16(dq_accum); one thread = 8 consecutive elements of one (b, row, h)
 __global__ void bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int H, int Nq,
-                                  int64_t sb, int64_t sr, int64_t sh, float scale) {
+                                  int64_t sb, int64_t sr, int64_t sh) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(B) * Nq * H * (kHeadDim / 8);
   if (idx >= total) return;
@@ -133,10 +143,10 @@ __global__ void bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* 
   const float4 a0 = *reinterpret_cast<const float4*>(acc + idx * 8);
   const float4 a1 = *reinterpret_cast<const float4*>(acc + idx * 8 + 4);
   uint4 out;
-  out.x = pack_bf16x2(a0.x * scale, a0.y * scale);
-  out.y = pack_bf16x2(a0.z * scale, a0.w * scale);
-  out.z = pack_bf16x2(a1.x * scale, a1.y * scale);
-  out.w = pack_bf16x2(a1.z * scale, a1.w * scale);
+  out.x = pack_bf16x2(a0.x, a0.y);
+  out.y = pack_bf16x2(a0.z, a0.w);
+  out.z = pack_bf16x2(a1.x, a1.y);
+  out.w = pack_bf16x2(a1.z, a1.w);
   *reinterpret_cast<uint4*>(dq + b * sb + row * sr + h * sh + c8 * 8) = out;
 }
 
@@ -305,8 +315,11 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (issuer) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tiles
       named_bar_sync(3, 128);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {          // 16-byte chunk c of the 256-byte fp32 row
-        uint4 val = make_uint4(r[c * 4], r[c * 4 + 1], r[c * 4 + 2], r[c * 4 + 3]);
+      for (int c = 0; c < 16; ++c) {          // 16-byte chunk c of the 256-byte fp32 row (softmax scale folded in)
+        uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[c * 4]) * p.scale),
+                               __float_as_uint(__uint_as_float(r[c * 4 + 1]) * p.scale),
+                               __float_as_uint(__uint_as_float(r[c * 4 + 2]) * p.scale),
+                               __float_as_uint(__uint_as_float(r[c * 4 + 3]) * p.scale));
         *reinterpret_cast<uint4*>(sm.dq_stage + (c >> 3) * kTileBytes + sw128_offset(row, c & 7)) = val;
       }
       fence_proxy_async_smem();
@@ -489,7 +502,7 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   const int nq_pad = static_cast<int>(align_up(static_cast<size_t>(a.Nq), kTile));
   const size_t acc_bytes = align_up(static_cast<size_t>(a.B) * a.Nq * a.H * kHeadDim * 4, 128);
   const size_t vec_bytes = align_up(static_cast<size_t>(a.B) * a.H * nq_pad * 4, 128);
-  float* dq_acc = reinterpret_cast<float*>(a.workspace);
+  float* dq_acc = a.accumulate_dq ? reinterpret_cast<float*>(a.dq) : reinterpret_cast<float*>(a.workspace);
   float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes);
   float* dsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes + vec_bytes);
 
@@ -506,12 +519,15 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
       return LCBI_ERR_TENSOR_MAP;
   }
 
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, acc_bytes, stream);
-  if (e != cudaSuccess) return set_cuda_error(e);
+  cudaError_t e = cudaSuccess;
+  if (!a.accumulate_dq) {
+    e = cudaMemsetAsync(dq_acc, 0, acc_bytes, stream);
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
   {
-    const int64_t warps = static_cast<int64_t>(a.B) * a.H * nq_pad;
+    const int64_t rows = static_cast<int64_t>(a.B) * a.H * nq_pad;
     const int threads = 256;
-    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    const int64_t blocks = (rows * 8 + threads - 1) / threads;
     bwd_prep_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(a.o), reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.lse, lse2, dsum,
         a.B, a.H, a.Nq, nq_pad, a.o_strides[0], a.o_strides[1], a.o_strides[2], a.do_strides[0], a.do_strides[1],
@@ -539,12 +555,12 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);
 
-  {
+  if (!a.accumulate_dq) {
     const int64_t total = static_cast<int64_t>(a.B) * a.Nq * a.H * (kHeadDim / 8);
     const int threads = 256;
     bwd_finish_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
         dq_acc, reinterpret_cast<__nv_bfloat16*>(a.dq), a.B, a.H, a.Nq, a.dq_strides[0], a.dq_strides[1],
-        a.dq_strides[2], a.scale);
+        a.dq_strides[2]);
     e = cudaGetLastError();
   }
   return set_cuda_error(e);

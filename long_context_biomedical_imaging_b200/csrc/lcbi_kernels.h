@@ -32,6 +32,7 @@ struct DenseAttnBwdArgs {
   int64_t dq_strides[3], dk_strides[3], dv_strides[3];
   float scale;
   int accumulate_dkv;   // 0: write bf16 dk/dv; 1: dk/dv are fp32 (B,Nk,H,d) contiguous accumulators (+=)
+  int accumulate_dq;    // 0: write bf16 dq;    1: dq is an fp32 (B,Nq,H,d) contiguous accumulator (+=)
 };
 size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
 int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream);
@@ -67,5 +68,9 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream);
 int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream);
 int window_maps_launch(int ndim, const int* grid, const int* window, const int* shift, int* gather, int* region,
                        int* relidx, int* n_out, int* nw_out, cudaStream_t stream);
+
+// ring-attention combine step (attn_merge.cu)
+int attn_merge_launch(float* acc, float* lse_acc, const void* o_s, const float* lse_s, void* out_bf16, int B, int N,
+                      int H, int head_dim, int first, cudaStream_t stream);
 
 }  // namespace lcbi

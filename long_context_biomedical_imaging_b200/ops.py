@@ -54,14 +54,17 @@ def dense_attn_fwd(q, k, v, scale, out=None):
     return o, lse
 
 
-def dense_attn_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None, accumulate_dkv=False):
-    """Gradients of dense_attn_fwd. With accumulate_dkv, dk/dv must be fp32 contiguous (B,Nk,H,d) buffers
-    that are accumulated into (ring steps)."""
+def dense_attn_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None, accumulate_dkv=False, accumulate_dq=False):
+    """Gradients of dense_attn_fwd. With accumulate_dkv (accumulate_dq), dk/dv (dq) must be fp32 contiguous
+    (B,N,H,d) buffers that are accumulated into (ring steps)."""
     _require_cuda(q, k, v, o, d_o, lse)
     B, Nq, H, d = q.shape
     Nk = k.shape[1]
     dev = q.device
-    if dq is None:
+    if accumulate_dq:
+        if dq is None or dq.dtype != torch.float32 or not dq.is_contiguous():
+            raise ValueError("accumulate_dq needs a contiguous fp32 dq accumulator")
+    elif dq is None:
         dq = torch.empty((B, Nq, H, d), dtype=torch.bfloat16, device=dev)
     if accumulate_dkv:
         if dk is None or dv is None or dk.dtype != torch.float32 or not dk.is_contiguous() or not dv.is_contiguous():
@@ -77,9 +80,21 @@ def dense_attn_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None, accum
     rc = lib.lcbi_dense_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(dq), _p(dk), _p(dv), B, H, Nq, Nk, d,
                                  _bnhd_strides(q), _bnhd_strides(k), _bnhd_strides(v), _bnhd_strides(o),
                                  _bnhd_strides(d_o), _bnhd_strides(dq), _bnhd_strides(dk), _bnhd_strides(dv),
-                                 float(scale), 1 if accumulate_dkv else 0, _p(ws), ws_bytes, _stream())
+                                 float(scale), 1 if accumulate_dkv else 0, 1 if accumulate_dq else 0, _p(ws), ws_bytes,
+                                 _stream())
     _lib.check(rc, "lcbi_dense_attn_bwd")
     return dq, dk, dv
+
+
+def attn_merge(acc, lse_acc, o_s, lse_s, first, out_bf16=None):
+    """Ring-attention combine: merges the partial (o_s, lse_s) into the running fp32 (acc, lse_acc) in place."""
+    _require_cuda(acc, lse_acc, o_s, lse_s)
+    B, N, H, d = acc.shape
+    if not (acc.is_contiguous() and o_s.is_contiguous() and lse_acc.is_contiguous() and lse_s.is_contiguous()):
+        raise ValueError("attn_merge expects contiguous tensors")
+    rc = _lib.load().lcbi_attn_merge(_p(acc), _p(lse_acc), _p(o_s), _p(lse_s), _p(out_bf16) if out_bf16 is not None else None,
+                                     B, N, H, d, 1 if first else 0, _stream())
+    _lib.check(rc, "lcbi_attn_merge")
 
 
 class _DenseAttentionQKV(torch.autograd.Function):
