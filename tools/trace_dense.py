@@ -1,0 +1,48 @@
+"""Debug: per-role clock64 timeline of CTA (0,0,0) of the dense forward kernel (needs the -DLCBI_TRACE build)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CSRC = os.path.join(ROOT, "long_context_biomedical_imaging_b200", "csrc")
+TRACE_LIB = os.path.join(CSRC, "liblcbi_b200_trace.so")
+
+
+def build():
+    srcs = [os.path.join(CSRC, f) for f in ("capi.cu", "dense_attn_fwd.cu", "dense_attn_bwd.cu", "window_attn.cu",
+                                            "patch_embed.cu", "attn_merge.cu")]
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-lineinfo",
+           "-DLCBI_TRACE", "-Xcompiler", "-fPIC", "-shared", "-o", TRACE_LIB] + srcs + ["-lcudart"]
+    subprocess.run(cmd, check=True)
+
+
+if __name__ == "__main__":
+    if sys.argv[1:] == ["build"]:
+        build()
+        sys.exit(0)
+    from long_context_biomedical_imaging_b200 import _lib
+    _lib.LIB_PATH = TRACE_LIB
+    from long_context_biomedical_imaging_b200 import ops
+    lib = _lib.load()
+    B, H, N, d = int(os.environ.get("TR_B", 16)), 12, 1728, 64
+    qkv = torch.randn(B, N, 3, H, d, device="cuda").to(torch.bfloat16)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    for _ in range(2):
+        ops.dense_attn_fwd(q, k, v, 0.125)
+    trace = torch.zeros(3 * 32 * 8, dtype=torch.int64, device="cuda")
+    lib.lcbi_debug_set_fwd_trace.argtypes = [ctypes.c_void_p]
+    assert lib.lcbi_debug_set_fwd_trace(ctypes.c_void_p(trace.data_ptr())) == 0
+    ops.dense_attn_fwd(q, k, v, 0.125)
+    torch.cuda.synchronize()
+    t = trace.cpu().view(3, 32, 8)
+    t0 = int(t[t > 0].min())
+    names = {0: "WG0", 1: "WG1", 2: "MMA"}
+    for role in range(3):
+        print(names[role])
+        for step in range(int(os.environ.get('TR_STEPS', 27))):
+            row = [int(x) - t0 if x > 0 else -1 for x in t[role, step]]
+            print(f"  step {step:2d}: " + " ".join(f"{x:7d}" for x in row))
