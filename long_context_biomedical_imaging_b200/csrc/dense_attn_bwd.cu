@@ -11,18 +11,21 @@
 //                 accumulator with a TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32).
 //   bwd_finish    dq = bf16(scale * dq_accum)
 //
-// bwd_main per query tile i (all five GEMMs on tcgen05, accumulators in TMEM, transposed formulation so that
-// the softmax threads own KEY rows and P^T / dS^T come out in the layout the next GEMM wants):
-//   S^T  = K  Q_i^T      A = K  (smem, K-major)        B = Q_i  (smem, K-major)      -> TMEM [0,128)
-//   dP^T = V  dO_i^T     A = V  (smem, K-major)        B = dO_i (smem, K-major)      -> TMEM [128,256)
-//   P^T  = exp2(S^T*c - lse2[q])            (bf16, written to TMEM [448,512))
-//   dS^T = P^T o (dP^T - D[q])              (bf16, written to a swizzled smem tile)
-//   dV  += P^T  dO_i     A = P^T (TMEM)                B = dO_i (smem, MN-major)     -> TMEM [256,320)
-//   dK  += dS^T Q_i      A = dS^T (smem, K-major)      B = Q_i  (smem, MN-major)     -> TMEM [320,384)
-//   dQ_i = dS   K        A = dS^T (smem, MN-major)     B = K    (smem, MN-major)     -> TMEM [384,448)
-// Warp roles (512 threads): warps 0-7 exponentiate / form dS (thread = key row x 64 query columns),
-// warps 8-11 drain dQ_i (TMEM -> swizzled fp32 smem -> TMA reduce-add), warp 12 TMA producer,
-// warp 13 UMMA issuer. Register file is rebalanced with setmaxnreg.
+// bwd_main pipelines 64-QUERY steps s (two per 128-query tile i); all five GEMMs run on tcgen05 with accumulators
+// in TMEM, in a transposed formulation so that the exponentiating threads own KEY rows and P^T / dS^T come out in
+// the layout the next GEMM wants. S^T, dP^T and P^T are double-buffered in TMEM, so the tensor core computes step
+// s+1's S^T / dP^T while the compute warps work on step s:
+//   S^T(s)  = K  Q_s^T     A = K  (smem, K-major)       B = Q_s  (smem, K-major)   -> TMEM [0,128)   (2 x 64)
+//   dP^T(s) = V  dO_s^T    A = V  (smem, K-major)       B = dO_s (smem, K-major)   -> TMEM [128,256) (2 x 64)
+//   one fused pass per step (warps 0-7, thread = key row x 32 query columns):
+//       P^T  = exp2(S^T*c - lse2[q])      -> bf16 -> TMEM [448,512) (2 x 32)
+//       dS^T = P^T o (dP^T - D[q])        -> bf16 -> swizzled smem atom of this step
+//   dV  += P^T(s)  dO_s    A = P^T (TMEM)               B = dO_s (smem, MN-major)  -> TMEM [256,320)
+//   dK  += dS^T(s) Q_s     A = dS^T atom (smem, K-major) B = Q_s (smem, MN-major)  -> TMEM [320,384)
+//   every second step:  dQ_i = dS(i) K   A = both dS^T atoms read MN-major, B = K (MN-major) -> TMEM [384,448)
+// Warp roles (512 threads): warps 0-7 compute, warps 8-11 drain dQ_i (TMEM -> x scale -> swizzled fp32 smem -> TMA
+// reduce-add), warp 12 TMA producer (Q/dO/lse2/D through 4-stage rings), warp 13 UMMA issuer (operand descriptors
+// are built once; only the start-address field advances per k-step).
 #include "lcbi_kernels.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
@@ -37,22 +40,46 @@ constexpr int kTileBytes = kTile * kHeadDim * 2;  // 16 KB
 constexpr int kNumThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
+constexpr int kStep = 64;                          // queries per pipeline step
+constexpr int kStepBytes = kStep * kHeadDim * 2;   // 8 KB
+constexpr int kQStages = 4;
+
+// TMEM columns: S^T and dP^T are double-buffered per 64-query step; P^T (bf16) likewise
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemP = 448;
 
 struct __align__(1024) BwdSmem {
   uint8_t k[kTileBytes];
   uint8_t v[kTileBytes];
-  uint8_t q[2][kTileBytes];      // also dK staging in the epilogue
-  uint8_t dout[2][kTileBytes];   // also dV staging in the epilogue
-  uint8_t ds[2 * kTileBytes];    // dS^T: two [128 keys x 64 queries] bf16 SW128 atoms
-  uint8_t dq_stage[2 * kTileBytes];  // two [128 queries x 32 fp32] SW128 tiles
-  float lse2[2][kTile];
-  float dsum[2][kTile];
+  uint8_t q[kQStages][kStepBytes];      // 64-query tiles; together also the dK staging area of the epilogue
+  uint8_t dout[kQStages][kStepBytes];   // likewise dV staging
+  uint8_t ds[2][2 * kTileBytes];        // dS^T per 128-query tile (double-buffered): two [128 keys x 64 queries] atoms
+  uint8_t dq_stage[2 * kTileBytes];     // two [128 queries x 32 fp32] SW128 tiles
+  float lse2[kQStages][kStep];
+  float dsum[kQStages][kStep];
   uint64_t kv_full;
-  uint64_t q_full[2], q_empty[2], do_full[2], do_empty[2];
-  uint64_t s_full, dp_full, p_full, ds_full, ds_empty, dq_full, dq_empty, dkv_full;
+  uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
+  uint64_t sdp_full[2], pds_full[2], ds_free[2], dq_full, dq_empty, dkv_full;
   uint32_t tmem_base;
 };
+
+#ifdef LCBI_TRACE
+__device__ long long* g_bwd_trace = nullptr;
+#define LCBI_TR_INIT() \
+  long long* const lcbi_tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_bwd_trace : nullptr
+#define LCBI_TR(role, step, ev)                                                            \
+  do {                                                                                     \
+    if (lcbi_tr != nullptr && (step) < 16) lcbi_tr[((role) * 16 + (step)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define LCBI_TR_INIT() do { } while (0)
+#define LCBI_TR(role, step, ev) do { } while (0)
+#endif
+
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 
 struct BwdParams {
   int B, H, Nq, Nk, Nq_pad;
@@ -153,6 +180,8 @@ __global__ void bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------
 // main
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+
 __global__ void __launch_bounds__(kNumThreads, 1)
 dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -166,23 +195,24 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int lane = tid & 31;
   const int kv_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
   const int kv_base = kv_tile * kTile;
-  const int n_q = p.Nq_pad / kTile;
+  const int n_steps = p.Nq_pad / kStep;      // 64-query steps; even because Nq_pad is a multiple of 128
+  LCBI_TR_INIT();
 
   if (tid == 0) {
     mbar_init(&sm.kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kQStages; ++s) {
       mbar_init(&sm.q_full[s], 1);
       mbar_init(&sm.q_empty[s], 1);
       mbar_init(&sm.do_full[s], 1);
       mbar_init(&sm.do_empty[s], 1);
     }
-    mbar_init(&sm.s_full, 1);
-    mbar_init(&sm.dp_full, 1);
-    mbar_init(&sm.p_full, 256);
-    mbar_init(&sm.ds_full, 256);
-    mbar_init(&sm.ds_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.sdp_full[b], 1);
+      mbar_init(&sm.pds_full[b], 8);   // one arrive per compute warp
+      mbar_init(&sm.ds_free[b], 1);
+    }
     mbar_init(&sm.dq_full, 1);
-    mbar_init(&sm.dq_empty, 128);
+    mbar_init(&sm.dq_empty, 4);        // one arrive per drain warp
     mbar_init(&sm.dkv_full, 1);
     fence_mbar_init();
   }
@@ -206,92 +236,88 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tma_load_4d(sm.v, &tm_v, &sm.kv_full, 0, head, kv_base, batch);
         const float* lse_row = p.lse2 + (static_cast<size_t>(batch) * p.H + head) * p.Nq_pad;
         const float* ds_row = p.dsum + (static_cast<size_t>(batch) * p.H + head) * p.Nq_pad;
-        for (int i = 0; i < n_q; ++i) {
-          const int st = i & 1;
-          const uint32_t ph = (i >> 1) & 1;
+        for (int s = 0; s < n_steps; ++s) {
+          const int st = s % kQStages;
+          const uint32_t ph = (s / kQStages) & 1;
           mbar_wait(&sm.q_empty[st], ph ^ 1);
-          mbar_expect_tx(&sm.q_full[st], kTileBytes + 2 * kTile * 4);
-          tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, i * kTile, batch);
-          bulk_load_1d(sm.lse2[st], lse_row + i * kTile, kTile * 4, &sm.q_full[st]);
-          bulk_load_1d(sm.dsum[st], ds_row + i * kTile, kTile * 4, &sm.q_full[st]);
+          mbar_expect_tx(&sm.q_full[st], kStepBytes + 2 * kStep * 4);
+          tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, s * kStep, batch);
+          bulk_load_1d(sm.lse2[st], lse_row + s * kStep, kStep * 4, &sm.q_full[st]);
+          bulk_load_1d(sm.dsum[st], ds_row + s * kStep, kStep * 4, &sm.q_full[st]);
           mbar_wait(&sm.do_empty[st], ph ^ 1);
-          mbar_expect_tx(&sm.do_full[st], kTileBytes);
-          tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, i * kTile, batch);
+          mbar_expect_tx(&sm.do_full[st], kStepBytes);
+          tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, s * kStep, batch);
         }
       }
     } else if (warp == 13) {
       // ---------------------------------------------------------------- UMMA issuer
       if (elect_one()) {
-        constexpr uint32_t idesc_nt = make_idesc_bf16(kTile, kTile, 0, 0);     // S^T, dP^T
-        constexpr uint32_t idesc_kmn = make_idesc_bf16(kTile, kHeadDim, 0, 1); // dV, dK: A K-major, B MN-major
-        constexpr uint32_t idesc_mnmn = make_idesc_bf16(kTile, kHeadDim, 1, 1);// dQ: A MN-major, B MN-major
-        const uint32_t k_addr = smem_u32(sm.k), v_addr = smem_u32(sm.v), ds_addr = smem_u32(sm.ds);
-        const uint32_t q_addr[2] = {smem_u32(sm.q[0]), smem_u32(sm.q[1])};
-        const uint32_t do_addr[2] = {smem_u32(sm.dout[0]), smem_u32(sm.dout[1])};
+        constexpr uint32_t idesc_nt = make_idesc_bf16(kTile, kStep, 0, 0);       // S^T, dP^T : 128 x 64
+        constexpr uint32_t idesc_kmn = make_idesc_bf16(kTile, kHeadDim, 0, 1);   // dV, dK: A K-major, B MN-major
+        constexpr uint32_t idesc_mnmn = make_idesc_bf16(kTile, kHeadDim, 1, 1);  // dQ: A MN-major, B MN-major
+        // loop-invariant operand descriptors (per k-step only the 14-bit start address field advances)
+        const uint64_t d_k = make_smem_desc(smem_u32(sm.k), 16, 1024, kLayoutSW128);
+        const uint64_t d_v = make_smem_desc(smem_u32(sm.v), 16, 1024, kLayoutSW128);
+        const uint64_t d_q0 = make_smem_desc(smem_u32(sm.q[0]), 16, 1024, kLayoutSW128);      // stages are contiguous
+        const uint64_t d_do0 = make_smem_desc(smem_u32(sm.dout[0]), 16, 1024, kLayoutSW128);
+        const uint64_t d_ds_k0 = make_smem_desc(smem_u32(sm.ds[0]), 16, 1024, kLayoutSW128);
+        const uint64_t d_ds_mn0 = make_smem_desc(smem_u32(sm.ds[0]), kTileBytes, 1024, kLayoutSW128);
 
-        auto gemm_nt = [&](uint32_t d_col, uint32_t a_addr, uint32_t b_addr) {
+        auto issue_sdp = [&](int s) {            // S^T(s) = K Q_s^T, dP^T(s) = V dO_s^T into buffer s & 1
+          const int st = s % kQStages, b = s & 1;
+          mbar_wait(&sm.q_full[st], (s / kQStages) & 1);
+          mbar_wait(&sm.do_full[st], (s / kQStages) & 1);
+          tc_fence_after();
+          const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
 #pragma unroll
           for (int kk = 0; kk < kHeadDim / 16; ++kk)
-            umma_ss(tmem + d_col, make_smem_desc(a_addr + kk * 32, 16, 1024, kLayoutSW128),
-                    make_smem_desc(b_addr + kk * 32, 16, 1024, kLayoutSW128), idesc_nt, kk > 0 ? 1u : 0u);
+            umma_ss(tmem + kTmemS + b * kStep, desc_advance(d_k, kk * 32), desc_advance(dq_s, kk * 32), idesc_nt,
+                    kk > 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)
+            umma_ss(tmem + kTmemDP + b * kStep, desc_advance(d_v, kk * 32), desc_advance(ddo_s, kk * 32), idesc_nt,
+                    kk > 0 ? 1u : 0u);
+          umma_commit(&sm.sdp_full[b]);
         };
 
         mbar_wait(&sm.kv_full, 0);
-        mbar_wait(&sm.q_full[0], 0);
-        tc_fence_after();
-        gemm_nt(kTmemS, k_addr, q_addr[0]);
-        umma_commit(&sm.s_full);
-        mbar_wait(&sm.do_full[0], 0);
-        tc_fence_after();
-        gemm_nt(kTmemDP, v_addr, do_addr[0]);
-        umma_commit(&sm.dp_full);
+        issue_sdp(0);
+        if (n_steps > 1) issue_sdp(1);
 
-        for (int i = 0; i < n_q; ++i) {
-          const int st = i & 1, nst = st ^ 1;
-          const uint32_t nph = ((i + 1) >> 1) & 1;
-          const bool more = (i + 1) < n_q;
-
-          // dV += P^T dO_i
-          mbar_wait(&sm.p_full, i & 1);
+        for (int s = 0; s < n_steps; ++s) {
+          const int st = s % kQStages, b = s & 1, i = s >> 1;
+          mbar_wait(&sm.pds_full[b], (s >> 1) & 1);
+          LCBI_TR(2, s, 0);
           tc_fence_after();
+          const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
+          const uint64_t dds_k = desc_advance(d_ds_k0, (i & 1) * 2 * kTileBytes + (s & 1) * kTileBytes);
+          // dV += P^T(s) dO_s   (A = bf16 P^T in TMEM, 64 queries = 4 k-steps)
 #pragma unroll
-          for (int kk = 0; kk < kTile / 16; ++kk)
-            umma_ts(tmem + kTmemDV, tmem + kTmemP + kk * 8,
-                    make_smem_desc(do_addr[st] + kk * 2048, 16, 1024, kLayoutSW128), idesc_kmn,
-                    (i > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kStep / 16; ++kk)
+            umma_ts(tmem + kTmemDV, tmem + kTmemP + b * 32 + kk * 8, desc_advance(ddo_s, kk * 2048), idesc_kmn,
+                    (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.do_empty[st]);
-          // S^T(i+1)
-          if (more) {
-            mbar_wait(&sm.q_full[nst], nph);
-            tc_fence_after();
-            gemm_nt(kTmemS, k_addr, q_addr[nst]);
-            umma_commit(&sm.s_full);
-          }
-          // dK += dS^T Q_i
-          mbar_wait(&sm.ds_full, i & 1);
-          tc_fence_after();
+          // dK += dS^T(s) Q_s   (A = this step's 64-query atom of the dS^T tile, K-major)
 #pragma unroll
-          for (int kk = 0; kk < kTile / 16; ++kk)
-            umma_ss(tmem + kTmemDK,
-                    make_smem_desc(ds_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128),
-                    make_smem_desc(q_addr[st] + kk * 2048, 16, 1024, kLayoutSW128), idesc_kmn,
-                    (i > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kStep / 16; ++kk)
+            umma_ss(tmem + kTmemDK, desc_advance(dds_k, kk * 32), desc_advance(dq_s, kk * 2048), idesc_kmn,
+                    (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.q_empty[st]);
-          // dQ_i = dS K
-          mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < kTile / 16; ++kk)
-            umma_ss(tmem + kTmemDQ, make_smem_desc(ds_addr + kk * 2048, kTileBytes, 1024, kLayoutSW128),
-                    make_smem_desc(k_addr + kk * 2048, 16, 1024, kLayoutSW128), idesc_mnmn, kk > 0 ? 1u : 0u);
-          umma_commit(&sm.dq_full);
-          umma_commit(&sm.ds_empty);
-          // dP^T(i+1)
-          if (more) {
-            mbar_wait(&sm.do_full[nst], nph);
+          LCBI_TR(2, s, 1);
+          if (s + 2 < n_steps) issue_sdp(s + 2);
+          LCBI_TR(2, s, 2);
+          if (s & 1) {
+            // dQ_i = dS(i) K over the whole 128-query tile (A = dS^T read MN-major: both atoms)
+            mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
             tc_fence_after();
-            gemm_nt(kTmemDP, v_addr, do_addr[nst]);
-            umma_commit(&sm.dp_full);
+            const uint64_t dds_mn = desc_advance(d_ds_mn0, (i & 1) * 2 * kTileBytes);
+#pragma unroll
+            for (int kk = 0; kk < kTile / 16; ++kk)
+              umma_ss(tmem + kTmemDQ, desc_advance(dds_mn, kk * 2048), desc_advance(d_k, kk * 2048), idesc_mnmn,
+                      kk > 0 ? 1u : 0u);
+            umma_commit(&sm.dq_full);
+            umma_commit(&sm.ds_free[i & 1]);
+            LCBI_TR(2, s, 3);
           }
         }
         umma_commit(&sm.dkv_full);
@@ -303,15 +329,18 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int row = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t t_dq = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kTmemDQ;
     const bool issuer = (tid == 8 * 32);
-    for (int i = 0; i < n_q; ++i) {
+    const int n_tiles = n_steps >> 1;
+    for (int i = 0; i < n_tiles; ++i) {
       mbar_wait(&sm.dq_full, i & 1);
+      if (issuer) LCBI_TR(3, i, 0);
       tc_fence_after();
       uint32_t r[64];
       tmem_ld_x32(t_dq, r);
       tmem_ld_x32(t_dq + 32, r + 32);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&sm.dq_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.dq_empty);
       if (issuer) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tiles
       named_bar_sync(3, 128);
 #pragma unroll
@@ -328,80 +357,69 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tma_reduce_add_4d(&tm_dqacc, sm.dq_stage, 0, head, i * kTile, batch);
         tma_reduce_add_4d(&tm_dqacc, sm.dq_stage + kTileBytes, 32, head, i * kTile, batch);
         tma_store_commit();
+        LCBI_TR(3, i, 1);
       }
     }
     if (issuer) tma_store_wait_all<0>();
   } else {
-    // ------------------------------------------------------------------ P^T / dS^T (warps 0-7)
+    // ------------------------------------------------------------------ P^T and dS^T in one pass (warps 0-7)
     setmaxnreg_inc<184>();
-    const int hh = warp >> 2;                   // which 64-query half of the tile this thread handles
+    const int hh = warp >> 2;                   // which 32-query half of the 64-query step this thread handles
     const int row = (warp & 3) * 32 + lane;     // key row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c = p.scale_log2;
 
-    for (int i = 0; i < n_q; ++i) {
-      const int st = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
-      float pr[64];
-      // ---- phase A: P^T = exp2(S^T * c - lse2[q])
-      mbar_wait(&sm.q_full[st], ph);   // lse2 / dsum of this tile visible
-      mbar_wait(&sm.s_full, i & 1);
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s % kQStages, b = s & 1, i = s >> 1;
+      if (lane == 0) LCBI_TR(hh, s, 0);
+      mbar_wait(&sm.q_full[st], (s / kQStages) & 1);          // lse2 / dsum of this step visible
+      mbar_wait(&sm.sdp_full[b], (s >> 1) & 1);
+      if ((s & 1) == 0) mbar_wait(&sm.ds_free[i & 1], ((i >> 1) & 1) ^ 1);   // dQ(i-2) has consumed this dS buffer
+      if (lane == 0) LCBI_TR(hh, s, 1);
       tc_fence_after();
+      uint32_t sv[32], dpv[32];
+      tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + hh * 32, sv);
+      tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
+      tmem_ld_wait();
+      if (lane == 0) LCBI_TR(hh, s, 2);
+      uint32_t pk[16];
+      uint8_t* ds_atom = sm.ds[i & 1] + (s & 1) * kTileBytes;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t s[32];
-        tmem_ld_x32(tmem + lane_sel + kTmemS + hh * 64 + ch * 32, s);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      for (int g = 0; g < 4; ++g) {             // 8 query columns -> one 16-byte chunk of dS^T
+        const float4 l0 = lds128(&sm.lse2[st][hh * 32 + g * 8]);
+        const float4 l1 = lds128(&sm.lse2[st][hh * 32 + g * 8 + 4]);
+        const float4 d0 = lds128(&sm.dsum[st][hh * 32 + g * 8]);
+        const float4 d1 = lds128(&sm.dsum[st][hh * 32 + g * 8 + 4]);
+        const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float pe[8], de[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 l4 = *reinterpret_cast<const float4*>(&sm.lse2[st][hh * 64 + ch * 32 + g * 4]);
-          const float e0 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 0]), c, -l4.x));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 1]), c, -l4.y));
-          const float e2 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 2]), c, -l4.z));
-          const float e3 = fast_exp2(fmaf(__uint_as_float(s[g * 4 + 3]), c, -l4.w));
-          pr[ch * 32 + g * 4 + 0] = e0;
-          pr[ch * 32 + g * 4 + 1] = e1;
-          pr[ch * 32 + g * 4 + 2] = e2;
-          pr[ch * 32 + g * 4 + 3] = e3;
-          pk[g * 2] = pack_bf16x2(e0, e1);
-          pk[g * 2 + 1] = pack_bf16x2(e2, e3);
+        for (int e = 0; e < 8; ++e) {
+          pe[e] = fast_exp2(fmaf(__uint_as_float(sv[g * 8 + e]), c, -lv[e]));
+          de[e] = pe[e] * (__uint_as_float(dpv[g * 8 + e]) - dv[e]);
         }
-        tmem_st_x16(tmem + lane_sel + kTmemP + hh * 32 + ch * 16, pk);
+        pk[g * 4 + 0] = pack_bf16x2(pe[0], pe[1]);
+        pk[g * 4 + 1] = pack_bf16x2(pe[2], pe[3]);
+        pk[g * 4 + 2] = pack_bf16x2(pe[4], pe[5]);
+        pk[g * 4 + 3] = pack_bf16x2(pe[6], pe[7]);
+        uint4 val;
+        val.x = pack_bf16x2(de[0], de[1]);
+        val.y = pack_bf16x2(de[2], de[3]);
+        val.z = pack_bf16x2(de[4], de[5]);
+        val.w = pack_bf16x2(de[6], de[7]);
+        *reinterpret_cast<uint4*>(ds_atom + sw128_offset(row, hh * 4 + g)) = val;
       }
+      tmem_st_x16(tmem + lane_sel + kTmemP + b * 32 + hh * 16, pk);
+      if (lane == 0) LCBI_TR(hh, s, 3);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&sm.p_full);
-
-      // ---- phase B: dS^T = P^T o (dP^T - D[q])
-      mbar_wait(&sm.dp_full, i & 1);
-      mbar_wait(&sm.ds_empty, (i & 1) ^ 1);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t dp[32];
-        tmem_ld_x32(tmem + lane_sel + kTmemDP + hh * 64 + ch * 32, dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {         // 8 query columns -> one 16-byte chunk
-          const float4 d0 = *reinterpret_cast<const float4*>(&sm.dsum[st][hh * 64 + ch * 32 + g * 8]);
-          const float4 d1 = *reinterpret_cast<const float4*>(&sm.dsum[st][hh * 64 + ch * 32 + g * 8 + 4]);
-          const float* pp = &pr[ch * 32 + g * 8];
-          const uint32_t* dd = &dp[g * 8];
-          uint4 val;
-          val.x = pack_bf16x2(pp[0] * (__uint_as_float(dd[0]) - d0.x), pp[1] * (__uint_as_float(dd[1]) - d0.y));
-          val.y = pack_bf16x2(pp[2] * (__uint_as_float(dd[2]) - d0.z), pp[3] * (__uint_as_float(dd[3]) - d0.w));
-          val.z = pack_bf16x2(pp[4] * (__uint_as_float(dd[4]) - d1.x), pp[5] * (__uint_as_float(dd[5]) - d1.y));
-          val.w = pack_bf16x2(pp[6] * (__uint_as_float(dd[6]) - d1.z), pp[7] * (__uint_as_float(dd[7]) - d1.w));
-          *reinterpret_cast<uint4*>(sm.ds + hh * kTileBytes + sw128_offset(row, ch * 4 + g)) = val;
-        }
-      }
-      tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&sm.ds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.pds_full[b]);
+      if (lane == 0) LCBI_TR(hh, s, 4);
     }
 
-    // ---- epilogue: hh == 0 drains dV, hh == 1 drains dK (scaled)
+    // ---- epilogue: warps 0-3 drain dV, warps 4-7 drain dK (scaled)
     mbar_wait(&sm.dkv_full, 0);
     tc_fence_after();
     uint32_t r[64];
@@ -410,7 +428,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tmem_ld_x32(t_src + 32, r + 32);
     tmem_ld_wait();
     const float mul = hh ? p.scale : 1.0f;
-    uint8_t* stage = hh ? sm.q[0] : sm.dout[0];   // 32 KB each (both stages), free once every MMA retired
+    uint8_t* stage = hh ? sm.q[0] : sm.dout[0];   // 32 KB each (all stages), free once every MMA retired
     const CUtensorMap* tm = hh ? &tm_dk : &tm_dv;
     if (!p.accumulate_dkv) {
 #pragma unroll
@@ -454,12 +472,12 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 13) tmem_dealloc(tmem, 512);
 }
 
-int make_bf16_map(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t* st) {
+int make_bf16_map(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t* st, int box_rows = kTile) {
   const uint64_t dims[4] = {static_cast<uint64_t>(kHeadDim), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
                             static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(st[2]) * 2, static_cast<uint64_t>(st[1]) * 2,
                                static_cast<uint64_t>(st[0]) * 2};
-  const uint32_t box[4] = {kHeadDim, 1, kTile, 1};
+  const uint32_t box[4] = {kHeadDim, 1, static_cast<uint32_t>(box_rows), 1};
   return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -476,6 +494,12 @@ int make_f32_acc_map(CUtensorMap* m, const void* base, int B, int H, int N) {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
+
+#ifdef LCBI_TRACE
+extern "C" int lcbi_debug_set_bwd_trace(long long* ptr) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_bwd_trace, &ptr, sizeof(ptr)));
+}
+#endif
 
 size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim) {
   const size_t nq_pad = align_up(static_cast<size_t>(Nq), kTile);
@@ -507,8 +531,8 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   float* dsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes + vec_bytes);
 
   CUtensorMap tq, tk, tv, tdo, tacc, tdk, tdv;
-  if (make_bf16_map(&tq, a.q, a.B, a.H, a.Nq, a.q_strides) || make_bf16_map(&tk, a.k, a.B, a.H, a.Nk, a.k_strides) ||
-      make_bf16_map(&tv, a.v, a.B, a.H, a.Nk, a.v_strides) || make_bf16_map(&tdo, a.d_o, a.B, a.H, a.Nq, a.do_strides) ||
+  if (make_bf16_map(&tq, a.q, a.B, a.H, a.Nq, a.q_strides, kStep) || make_bf16_map(&tk, a.k, a.B, a.H, a.Nk, a.k_strides) ||
+      make_bf16_map(&tv, a.v, a.B, a.H, a.Nk, a.v_strides) || make_bf16_map(&tdo, a.d_o, a.B, a.H, a.Nq, a.do_strides, kStep) ||
       make_f32_acc_map(&tacc, dq_acc, a.B, a.H, a.Nq))
     return LCBI_ERR_TENSOR_MAP;
   if (a.accumulate_dkv) {

@@ -38,6 +38,24 @@ if __name__ == "__main__":
     assert lib.lcbi_debug_set_fwd_trace(ctypes.c_void_p(trace.data_ptr())) == 0
     ops.dense_attn_fwd(q, k, v, 0.125)
     torch.cuda.synchronize()
+    if os.environ.get("TR_BWD"):
+        o, lse = ops.dense_attn_fwd(q, k, v, 0.125)
+        d_o = torch.randn_like(o)
+        for _ in range(2):
+            ops.dense_attn_bwd(q, k, v, o, d_o, lse, 0.125)
+        btrace = torch.zeros(4 * 16 * 8, dtype=torch.int64, device="cuda")
+        lib.lcbi_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
+        assert lib.lcbi_debug_set_bwd_trace(ctypes.c_void_p(btrace.data_ptr())) == 0
+        ops.dense_attn_bwd(q, k, v, o, d_o, lse, 0.125)
+        torch.cuda.synchronize()
+        bt = btrace.cpu().view(4, 16, 8)
+        t0 = int(bt[bt > 0].min())
+        for role, name in enumerate(["CMP half0", "CMP half1", "MMA", "DRAIN"]):
+            print(name)
+            for step in range(16):
+                row = [int(x) - t0 if x > 0 else -1 for x in bt[role, step]]
+                print(f"  tile {step:2d}: " + " ".join(f"{x:7d}" for x in row))
+        sys.exit(0)
     t = trace.cpu().view(3, 32, 8)
     t0 = int(t[t > 0].min())
     names = {0: "WG0", 1: "WG1", 2: "MMA"}
