@@ -44,8 +44,11 @@ constexpr int kStep = 64;                          // queries per pipeline step
 constexpr int kStepBytes = kStep * kHeadDim * 2;   // 8 KB
 constexpr int kQStages = 4;
 
-// TMEM columns: S^T and dP^T are double-buffered per 64-query step; P^T (bf16) likewise
-constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemP = 448;
+// TMEM columns: S^T and dP^T are double-buffered per 64-query step; the bf16 P^T / dS^T of a step overwrite, in
+// place, the first half of the columns their owner thread read (thread (row, hh) owns columns [32hh, 32hh+32) of a
+// buffer and writes 16 packed columns at [32hh, 32hh+16)); K and V sit in TMEM as the A operands of S^T / dP^T.
+constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemK = 448, kTmemV = 480;
+constexpr bool kDrainWithRed = false;   // dQ partials: red.global.add.v4.f32 from registers (no smem staging)
 
 struct __align__(1024) BwdSmem {
   uint8_t k[kTileBytes];
@@ -58,7 +61,7 @@ struct __align__(1024) BwdSmem {
   float dsum[kQStages][kStep];
   uint64_t kv_full;
   uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
-  uint64_t sdp_full[2], pds_full[2], ds_free[2], dq_full, dq_empty, dkv_full;
+  uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full;
   uint32_t tmem_base;
 };
 
@@ -86,6 +89,7 @@ struct BwdParams {
   float scale, scale_log2;
   const float* lse2;   // (B,H,Nq_pad)
   const float* dsum;   // (B,H,Nq_pad)
+  float* dq_acc;       // fp32 (B,Nq,H,64) accumulator
   int accumulate_dkv;
 };
 
@@ -209,8 +213,8 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.sdp_full[b], 1);
       mbar_init(&sm.pds_full[b], 8);   // one arrive per compute warp
-      mbar_init(&sm.ds_free[b], 1);
     }
+    mbar_init(&sm.kvt_full, 8);
     mbar_init(&sm.dq_full, 1);
     mbar_init(&sm.dq_empty, 4);        // one arrive per drain warp
     mbar_init(&sm.dkv_full, 1);
@@ -257,10 +261,8 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         constexpr uint32_t idesc_mnmn = make_idesc_bf16(kTile, kHeadDim, 1, 1);  // dQ: A MN-major, B MN-major
         // loop-invariant operand descriptors (per k-step only the 14-bit start address field advances)
         const uint64_t d_k = make_smem_desc(smem_u32(sm.k), 16, 1024, kLayoutSW128);
-        const uint64_t d_v = make_smem_desc(smem_u32(sm.v), 16, 1024, kLayoutSW128);
         const uint64_t d_q0 = make_smem_desc(smem_u32(sm.q[0]), 16, 1024, kLayoutSW128);      // stages are contiguous
         const uint64_t d_do0 = make_smem_desc(smem_u32(sm.dout[0]), 16, 1024, kLayoutSW128);
-        const uint64_t d_ds_k0 = make_smem_desc(smem_u32(sm.ds[0]), 16, 1024, kLayoutSW128);
         const uint64_t d_ds_mn0 = make_smem_desc(smem_u32(sm.ds[0]), kTileBytes, 1024, kLayoutSW128);
 
         auto issue_sdp = [&](int s) {            // S^T(s) = K Q_s^T, dP^T(s) = V dO_s^T into buffer s & 1
@@ -270,17 +272,19 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tc_fence_after();
           const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
 #pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk)
-            umma_ss(tmem + kTmemS + b * kStep, desc_advance(d_k, kk * 32), desc_advance(dq_s, kk * 32), idesc_nt,
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
+            umma_ts(tmem + kTmemS + b * kStep, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt,
                     kk > 0 ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk)
-            umma_ss(tmem + kTmemDP + b * kStep, desc_advance(d_v, kk * 32), desc_advance(ddo_s, kk * 32), idesc_nt,
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = V from TMEM
+            umma_ts(tmem + kTmemDP + b * kStep, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt,
                     kk > 0 ? 1u : 0u);
           umma_commit(&sm.sdp_full[b]);
         };
 
         mbar_wait(&sm.kv_full, 0);
+        mbar_wait(&sm.kvt_full, 0);      // K, V copied into TMEM by the compute warps
+        tc_fence_after();
         issue_sdp(0);
         if (n_steps > 1) issue_sdp(1);
 
@@ -290,18 +294,18 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           LCBI_TR(2, s, 0);
           tc_fence_after();
           const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
-          const uint64_t dds_k = desc_advance(d_ds_k0, (i & 1) * 2 * kTileBytes + (s & 1) * kTileBytes);
-          // dV += P^T(s) dO_s   (A = bf16 P^T in TMEM, 64 queries = 4 k-steps)
+          // dV += P^T(s) dO_s   (A = bf16 P^T, in place in the S buffer: 16 queries = 8 columns per k-step, the
+          //                      two 32-query halves start at columns 0 and 32)
 #pragma unroll
           for (int kk = 0; kk < kStep / 16; ++kk)
-            umma_ts(tmem + kTmemDV, tmem + kTmemP + b * 32 + kk * 8, desc_advance(ddo_s, kk * 2048), idesc_kmn,
-                    (s > 0 || kk > 0) ? 1u : 0u);
+            umma_ts(tmem + kTmemDV, tmem + kTmemS + b * kStep + (kk >> 1) * 32 + (kk & 1) * 8,
+                    desc_advance(ddo_s, kk * 2048), idesc_kmn, (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.do_empty[st]);
-          // dK += dS^T(s) Q_s   (A = this step's 64-query atom of the dS^T tile, K-major)
+          // dK += dS^T(s) Q_s   (A = bf16 dS^T, in place in the dP buffer)
 #pragma unroll
           for (int kk = 0; kk < kStep / 16; ++kk)
-            umma_ss(tmem + kTmemDK, desc_advance(dds_k, kk * 32), desc_advance(dq_s, kk * 2048), idesc_kmn,
-                    (s > 0 || kk > 0) ? 1u : 0u);
+            umma_ts(tmem + kTmemDK, tmem + kTmemDP + b * kStep + (kk >> 1) * 32 + (kk & 1) * 8,
+                    desc_advance(dq_s, kk * 2048), idesc_kmn, (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.q_empty[st]);
           LCBI_TR(2, s, 1);
           if (s + 2 < n_steps) issue_sdp(s + 2);
@@ -316,7 +320,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               umma_ss(tmem + kTmemDQ, desc_advance(dds_mn, kk * 2048), desc_advance(d_k, kk * 2048), idesc_mnmn,
                       kk > 0 ? 1u : 0u);
             umma_commit(&sm.dq_full);
-            umma_commit(&sm.ds_free[i & 1]);
             LCBI_TR(2, s, 3);
           }
         }
@@ -341,6 +344,21 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.dq_empty);
+      if constexpr (kDrainWithRed) {
+        // each thread adds its own 256-byte dQ row straight into the fp32 accumulator (16 x red.v4.f32)
+        const int q_row = i * kTile + row;
+        if (q_row < p.Nq) {
+          float* dst = p.dq_acc + ((static_cast<size_t>(batch) * p.Nq + q_row) * p.H + head) * kHeadDim;
+#pragma unroll
+          for (int c4 = 0; c4 < 16; ++c4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c4 * 4),
+                         "f"(__uint_as_float(r[c4 * 4]) * p.scale), "f"(__uint_as_float(r[c4 * 4 + 1]) * p.scale),
+                         "f"(__uint_as_float(r[c4 * 4 + 2]) * p.scale), "f"(__uint_as_float(r[c4 * 4 + 3]) * p.scale)
+                         : "memory");
+        }
+        if (issuer) LCBI_TR(3, i, 1);
+        continue;
+      }
       if (issuer) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tiles
       named_bar_sync(3, 128);
 #pragma unroll
@@ -369,12 +387,29 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c = p.scale_log2;
 
+    // K (warps 0-3) and V (warps 4-7) rows -> TMEM: they are the A operands of every S^T / dP^T GEMM of this CTA
+    {
+      mbar_wait(&sm.kv_full, 0);
+      const uint8_t* src = hh ? sm.v : sm.k;
+      uint32_t kv[32];
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        const uint4 x = *reinterpret_cast<const uint4*>(src + sw128_offset(row, c16));
+        kv[c16 * 4 + 0] = x.x; kv[c16 * 4 + 1] = x.y; kv[c16 * 4 + 2] = x.z; kv[c16 * 4 + 3] = x.w;
+      }
+      tmem_st_x32(tmem + lane_sel + (hh ? kTmemV : kTmemK), kv);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.kvt_full);
+    }
+
     for (int s = 0; s < n_steps; ++s) {
       const int st = s % kQStages, b = s & 1, i = s >> 1;
       if (lane == 0) LCBI_TR(hh, s, 0);
-      mbar_wait(&sm.q_full[st], (s / kQStages) & 1);          // lse2 / dsum of this step visible
+      // One wait per step: the issuer waited on q_full/do_full before the GEMMs this commit covers (so lse2 / dsum
+      // of the step are in smem), and the commit also covers dQ(i-2), the last reader of the dS^T smem buffer.
       mbar_wait(&sm.sdp_full[b], (s >> 1) & 1);
-      if ((s & 1) == 0) mbar_wait(&sm.ds_free[i & 1], ((i >> 1) & 1) ^ 1);   // dQ(i-2) has consumed this dS buffer
       if (lane == 0) LCBI_TR(hh, s, 1);
       tc_fence_after();
       uint32_t sv[32], dpv[32];
@@ -382,16 +417,21 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
       tmem_ld_wait();
       if (lane == 0) LCBI_TR(hh, s, 2);
-      uint32_t pk[16];
+      uint32_t pk[16], dsk[16];
       uint8_t* ds_atom = sm.ds[i & 1] + (s & 1) * kTileBytes;
+      // per-query lse2 / dsum: software-pipelined broadcast loads (next group's values in flight while this one computes)
+      float4 l0 = lds128(&sm.lse2[st][hh * 32]), l1 = lds128(&sm.lse2[st][hh * 32 + 4]);
+      float4 d0 = lds128(&sm.dsum[st][hh * 32]), d1 = lds128(&sm.dsum[st][hh * 32 + 4]);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {             // 8 query columns -> one 16-byte chunk of dS^T
-        const float4 l0 = lds128(&sm.lse2[st][hh * 32 + g * 8]);
-        const float4 l1 = lds128(&sm.lse2[st][hh * 32 + g * 8 + 4]);
-        const float4 d0 = lds128(&sm.dsum[st][hh * 32 + g * 8]);
-        const float4 d1 = lds128(&sm.dsum[st][hh * 32 + g * 8 + 4]);
         const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        if (g < 3) {
+          l0 = lds128(&sm.lse2[st][hh * 32 + (g + 1) * 8]);
+          l1 = lds128(&sm.lse2[st][hh * 32 + (g + 1) * 8 + 4]);
+          d0 = lds128(&sm.dsum[st][hh * 32 + (g + 1) * 8]);
+          d1 = lds128(&sm.dsum[st][hh * 32 + (g + 1) * 8 + 4]);
+        }
         float pe[8], de[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -402,14 +442,18 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         pk[g * 4 + 1] = pack_bf16x2(pe[2], pe[3]);
         pk[g * 4 + 2] = pack_bf16x2(pe[4], pe[5]);
         pk[g * 4 + 3] = pack_bf16x2(pe[6], pe[7]);
-        uint4 val;
-        val.x = pack_bf16x2(de[0], de[1]);
-        val.y = pack_bf16x2(de[2], de[3]);
-        val.z = pack_bf16x2(de[4], de[5]);
-        val.w = pack_bf16x2(de[6], de[7]);
-        *reinterpret_cast<uint4*>(ds_atom + sw128_offset(row, hh * 4 + g)) = val;
+        dsk[g * 4 + 0] = pack_bf16x2(de[0], de[1]);
+        dsk[g * 4 + 1] = pack_bf16x2(de[2], de[3]);
+        dsk[g * 4 + 2] = pack_bf16x2(de[4], de[5]);
+        dsk[g * 4 + 3] = pack_bf16x2(de[6], de[7]);
       }
-      tmem_st_x16(tmem + lane_sel + kTmemP + b * 32 + hh * 16, pk);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
+                     "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
+      // in place: the packed results overwrite the first 16 of the 32 columns this thread just read
+      tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + hh * 32, pk);
+      tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dsk);
       if (lane == 0) LCBI_TR(hh, s, 3);
       tmem_st_wait();
       tc_fence_before();
@@ -573,6 +617,7 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * kLog2e;
   p.lse2 = lse2;
   p.dsum = dsum;
+  p.dq_acc = dq_acc;
   p.accumulate_dkv = a.accumulate_dkv;
   dim3 grid((a.Nk + kTile - 1) / kTile, a.H, a.B);
   dense_attn_bwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, tdo, tacc, tdk, tdv, p);
