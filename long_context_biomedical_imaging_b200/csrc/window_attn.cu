@@ -477,12 +477,13 @@ size_t dkdv_smem_bytes(const WinGeom& g, int D) {
 //   CTA = (head, 32-row query slab, window subset); warp (qt, ks) = 16-row query tile x 128-key split.
 //   Loops over its windows keeping dBias[32 x n] for the slab in registers; per window dQ = dS K.
 // =================================================================================================
-constexpr int kSlabRows = 32;
 constexpr int kKeySplit = 128;
 
-template <int D>
-__global__ void __launch_bounds__(256)
+// QT = 16-row query tiles per CTA (slab = 16*QT rows), MAXKS = max number of 128-key splits (block = 32*QT*n_ks)
+template <int D, int QT, int MAXKS>
+__global__ void __launch_bounds__(32 * QT * MAXKS)
 win_attn_bwd_dq_kernel(const WinParams p) {
+  constexpr int kSlabRows = 16 * QT;
   extern __shared__ __align__(16) uint8_t smem[];
   const WinGeom& g = p.g;
   const int n = g.n, n_pad = round_up(n, kKeySplit);
@@ -504,7 +505,7 @@ win_attn_bwd_dq_kernel(const WinParams p) {
   meta.col_term = meta.row_term + n_pad;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qt = warp & 1, ks = warp >> 1;
+  const int qt = warp % QT, ks = warp / QT;
   const int slab = blockIdx.x, h = blockIdx.y, split = blockIdx.z;
   const int row_base = slab * kSlabRows;          // first window slot of this slab
   const int gq = lane >> 2, qq = lane & 3;
@@ -575,8 +576,10 @@ win_attn_bwd_dq_kernel(const WinParams p) {
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
 
+    const int n_sub = min(4, (n - ks * kKeySplit + 31) / 32);   // 32-key steps of this split that hold real keys
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {            // 32 keys per step inside this warp's 128-key split
+      if (sub >= n_sub) break;
       const int key0 = ks * kKeySplit + sub * 32;
       float s[4][4], dp[4][4];
 #pragma unroll
@@ -675,11 +678,11 @@ win_attn_bwd_dq_kernel(const WinParams p) {
   }
 }
 
-size_t dq_smem_bytes(const WinGeom& g, int D) {
+size_t dq_smem_bytes(const WinGeom& g, int D, int slab_rows) {
   const int n_pad = round_up(g.n, kKeySplit);
   const int n_ks = n_pad / kKeySplit;
-  return static_cast<size_t>(2) * n_pad * (D * 2 + 16) + static_cast<size_t>(2) * kSlabRows * (D * 2 + 16) +
-         static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 + 2 * kSlabRows * 4 + static_cast<size_t>(n_ks) * kSlabRows * D * 4 +
+  return static_cast<size_t>(2) * n_pad * (D * 2 + 16) + static_cast<size_t>(2) * slab_rows * (D * 2 + 16) +
+         static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 + 2 * slab_rows * 4 + static_cast<size_t>(n_ks) * slab_rows * D * 4 +
          static_cast<size_t>(n_pad) * 16;
 }
 
@@ -762,25 +765,31 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
   }
-  // 3. dQ (+ bias-table gradient)
+  // 3. dQ (+ bias-table gradient): 64-row slabs (4 query tiles) up to 384-token windows, 32-row slabs above
   {
-    const size_t smem = dq_smem_bytes(p.g, D);
-    const int n_slabs = (p.g.n + kSlabRows - 1) / kSlabRows;
     const int n_ks = round_up(p.g.n, kKeySplit) / kKeySplit;
+    const int qt = (n_ks <= 3) ? 4 : 2;
+    const int slab_rows = 16 * qt;
+    const size_t smem = dq_smem_bytes(p.g, D, slab_rows);
+    const int n_slabs = (p.g.n + slab_rows - 1) / slab_rows;
     const int total_windows = p.B * p.g.nW;
-    int splits = (4 * 148 + n_slabs * p.H - 1) / (n_slabs * p.H);   // aim at ~4 CTAs per SM
+    int splits = (6 * 148 + n_slabs * p.H - 1) / (n_slabs * p.H);   // aim at ~6 CTAs' worth of work per SM
     if (splits > total_windows) splits = total_windows;
     if (splits < 1) splits = 1;
     p.win_splits = splits;
     dim3 grid(n_slabs, p.H, splits);
-    const int threads = 64 * n_ks;
+    const int threads = 32 * qt * n_ks;
+#define LCBI_DQ_LAUNCH(DD, QQ, KK)                                                       \
+  do {                                                                                   \
+    if ((rc = set_smem(win_attn_bwd_dq_kernel<DD, QQ, KK>, smem))) return rc;            \
+    win_attn_bwd_dq_kernel<DD, QQ, KK><<<grid, threads, smem, stream>>>(p);              \
+  } while (0)
     if (D == 16) {
-      if ((rc = set_smem(win_attn_bwd_dq_kernel<16>, smem))) return rc;
-      win_attn_bwd_dq_kernel<16><<<grid, threads, smem, stream>>>(p);
+      if (qt == 4) LCBI_DQ_LAUNCH(16, 4, 3); else LCBI_DQ_LAUNCH(16, 2, 4);
     } else {
-      if ((rc = set_smem(win_attn_bwd_dq_kernel<32>, smem))) return rc;
-      win_attn_bwd_dq_kernel<32><<<grid, threads, smem, stream>>>(p);
+      if (qt == 4) LCBI_DQ_LAUNCH(32, 4, 3); else LCBI_DQ_LAUNCH(32, 2, 4);
     }
+#undef LCBI_DQ_LAUNCH
   }
   return set_cuda_error(cudaGetLastError());
 }
