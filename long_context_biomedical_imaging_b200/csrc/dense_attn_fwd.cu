@@ -239,16 +239,13 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // faster (0.276 ms vs 0.300 ms at cfg3 B=16). Kept for experiments, off by default.
       const bool pingpong = kExpPingPong && tile1_active;
       if (pingpong && t == 1) named_bar_arrive(3, 256);
-      // Both groups would otherwise run in lock-step (their first S tiles complete together) and hit the MUFU-bound
-      // exp phase and the MUFU-idle load/max/store phases at the same time; a one-off half-period offset lets one
-      // group's exponentials cover the other's bookkeeping for the rest of the loop.
-      if (kStaggerNs > 0 && t == 1) __nanosleep(kStaggerNs);
 
       for (int j = 0; j < n_kv; ++j) {
         const int buf = j & 1;
         const uint32_t t_s = tmem + lane_sel + tmem_s(t, buf);
         if (row == 0) LCBI_TR(t, j, 0);
         mbar_wait(&sm.s_full[t][buf], (j >> 1) & 1);
+        if (kStaggerNs > 0 && t == 1 && j == 0) __nanosleep(kStaggerNs);   // one-off phase offset between the groups
         if (row == 0) LCBI_TR(t, j, 1);
         tc_fence_after();
         uint32_t sr[64];

@@ -14,40 +14,17 @@
 // These kernels use warp-level mma.sync tiles: head_dim is 16 or 32 and windows hold 49..512 tokens, so the
 // work per (window, head) is far below a tcgen05 tile; the bound is HBM traffic / exp throughput, not the
 // tensor pipe ("window attention roofline").
+#include <cstdlib>
+
 #include "lcbi_kernels.h"
 #include "window_common.cuh"
 
 namespace lcbi {
 
+int win_attn_fwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream);   // window_attn_small.cu
+int win_attn_bwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream);   // window_attn_small.cu
+
 namespace {
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kKeyChunk = 64;
-
-struct WinParams {
-  WinGeom g;
-  int B, H, C;
-  float scale_log2;             // head_dim^-0.5 * log2(e)
-  const __nv_bfloat16* qkv;     // (B, T, 3, H, D)
-  const float* qkv_bias;        // (3*C) or nullptr
-  const float* table;           // (tab_rows, H)
-  __nv_bfloat16* out;           // (B, T, C)                      [fwd]
-  float* lse2;                  // (B, T, H) log2-domain logsumexp [fwd out / bwd in]
-  // backward
-  const __nv_bfloat16* d_out;   // (B, T, C)
-  const float* dsum;            // (B, T, H) rowsum(dO o O)
-  __nv_bfloat16* dqkv;          // (B, T, 3, H, D)
-  float* dbias_pad;             // (3*C) fp32, += gradient reaching qkv.bias through the pad tokens
-  float* dtable;                // (tab_rows, H) fp32, +=
-  int win_splits;               // dq kernel: number of window subsets
-};
-
-template <int D>
-struct Tile {
-  static constexpr int kStride = D * 2 + 16;   // bytes per smem row: +16 keeps ldmatrix conflict-free
-};
-
-__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // -------------------------------------------------------------------------------------------------
 // per-CTA window metadata in shared memory
@@ -104,8 +81,11 @@ __device__ __forceinline__ void load_rows(uint8_t* tile, const WinParams& p, con
 // =================================================================================================
 // forward: CTA = (window, head), 4 warps, each warp owns 16-row query tiles
 // =================================================================================================
-template <int D>
-__global__ void __launch_bounds__(128)
+// kHighOcc: cap registers for 6 (D=32: a few spills) CTAs per SM. Measured on B200: a win when the window is one
+// key chunk (n <= 64: the kernel is latency-bound, 235 -> 192 us at cfg2 stage 1) and for d = 16; a loss for
+// d = 32 with 343-token windows, where the spills land in the six-iteration key loop.
+template <int D, bool kHighOcc>
+__global__ void __launch_bounds__(128, kHighOcc ? 6 : 1)
 win_attn_fwd_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const WinGeom& g = p.g;
@@ -306,8 +286,8 @@ __device__ __forceinline__ void load_row_scalars(const WinParams& p, const int* 
 // backward dK/dV: CTA = (window, head), 4 warps, each warp owns 16-row KEY tiles and sweeps the queries
 //   S^T = K Q^T, P^T = exp2(.), dP^T = V dO^T, dS^T = P^T o (dP^T - D[q]); dV += P^T dO; dK += dS^T Q
 // =================================================================================================
-template <int D>
-__global__ void __launch_bounds__(128)
+template <int D, bool kHighOcc>
+__global__ void __launch_bounds__(128, kHighOcc ? 5 : 1)
 win_attn_bwd_dkdv_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const WinGeom& g = p.g;
@@ -723,14 +703,21 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
   WinParams p;
   int rc = fill_params(p, a);
   if (rc) return rc;
+  // experimental warp-per-window persistent kernel for <= 64-token windows (window_attn_small.cu); measured slower
+  // than the CTA-per-(window, head) kernel on B200 (8 warps/SM cannot hide its latency), so it is opt-in
+  static const bool use_small = std::getenv("LCBI_WIN_SMALL") != nullptr;
+  if (use_small && p.g.n <= 64) return win_attn_fwd_small_launch(p, a.head_dim, stream);
   const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
   dim3 grid(p.B * p.g.nW, p.H);
   if (a.head_dim == 16) {
-    if ((rc = set_smem(win_attn_fwd_kernel<16>, smem))) return rc;
-    win_attn_fwd_kernel<16><<<grid, 128, smem, stream>>>(p);
+    if ((rc = set_smem(win_attn_fwd_kernel<16, true>, smem))) return rc;
+    win_attn_fwd_kernel<16, true><<<grid, 128, smem, stream>>>(p);
+  } else if (p.g.n <= 64) {
+    if ((rc = set_smem(win_attn_fwd_kernel<32, true>, smem))) return rc;
+    win_attn_fwd_kernel<32, true><<<grid, 128, smem, stream>>>(p);
   } else {
-    if ((rc = set_smem(win_attn_fwd_kernel<32>, smem))) return rc;
-    win_attn_fwd_kernel<32><<<grid, 128, smem, stream>>>(p);
+    if ((rc = set_smem(win_attn_fwd_kernel<32, false>, smem))) return rc;
+    win_attn_fwd_kernel<32, false><<<grid, 128, smem, stream>>>(p);
   }
   return set_cuda_error(cudaGetLastError());
 }
@@ -751,16 +738,22 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
   }
+  // small windows (<= 64 tokens): one fused kernel produces dq, dk, dv, the pad-token bias gradient and d(table)
+  static const bool legacy_small_bwd = std::getenv("LCBI_WIN_LEGACY_BWD") != nullptr;
+  if (p.g.n <= 64 && !legacy_small_bwd) return win_attn_bwd_small_launch(p, D, stream);
   // 2. dK, dV (+ pad-token bias gradient)
   {
     const size_t smem = dkdv_smem_bytes(p.g, D);
     dim3 grid(p.B * p.g.nW, p.H);
     if (D == 16) {
-      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16>, smem))) return rc;
-      win_attn_bwd_dkdv_kernel<16><<<grid, 128, smem, stream>>>(p);
+      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16, true>, smem))) return rc;
+      win_attn_bwd_dkdv_kernel<16, true><<<grid, 128, smem, stream>>>(p);
+    } else if (p.g.n <= 64) {
+      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32, true>, smem))) return rc;
+      win_attn_bwd_dkdv_kernel<32, true><<<grid, 128, smem, stream>>>(p);
     } else {
-      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32>, smem))) return rc;
-      win_attn_bwd_dkdv_kernel<32><<<grid, 128, smem, stream>>>(p);
+      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32, false>, smem))) return rc;
+      win_attn_bwd_dkdv_kernel<32, false><<<grid, 128, smem, stream>>>(p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);

@@ -1,0 +1,580 @@
+// Swin window attention forward for SMALL windows (<= 64 tokens: 7x7, 8x8, 4x4x4, clamped windows).
+//
+// Same operation as win_attn_fwd_kernel (window_attn.cu) — the reference's forward_part1 gather / attention core
+// / scatter, /root/reference/model/models/backbone_swin.py:339-357, :441-485, :591-628 — but organised for the
+// regime where a whole (window, head) fits one warp and the per-element bias / mask bookkeeping, not the MMAs,
+// dominates the instruction count:
+//   * persistent CTAs, one per (head, slice of the window list): 8 warps, each warp owns one (window, head) at a
+//     time — no block-level synchronisation inside the loop, the warps' load and compute phases interleave;
+//   * the relative-position bias of the head is expanded ONCE per CTA into a 64 x 64 fp32 shared-memory tile
+//     (already multiplied by log2 e, -inf in the columns beyond the window), so the inner loop adds it with one
+//     conflict-free 8-byte load per two logits instead of re-deriving table indices;
+//   * the shift-mask test runs only for windows that actually straddle a shift boundary (warp vote on the region
+//     ids); interior windows skip it;
+//   * K and V fragments are loaded to registers once per window and reused by the four 16-row query tiles.
+#include "lcbi_kernels.h"
+#include "window_common.cuh"
+
+namespace lcbi {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kBiasStride = 72;   // floats per bias-tile row: 8-byte loads of a quad pattern hit 16 distinct bank pairs
+
+template <int D>
+struct SmallSmem {
+  static constexpr int kStride = Tile<D>::kStride;
+  static constexpr int kTileBytes = 64 * kStride;
+  static constexpr int kPerWarp = 3 * kTileBytes + 2 * 64 * 4;   // Q, K, V tiles + tok[64] + reg[64]
+  static constexpr int kBiasBytes = 64 * kBiasStride * 4;
+  static constexpr int kTotal = kBiasBytes + kWarps * kPerWarp;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kWarps * 32)
+win_attn_fwd_small_kernel(const WinParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  using L = SmallSmem<D>;
+  constexpr int kStride = L::kStride;
+  constexpr int kChunks = D / 8;
+  const WinGeom& g = p.g;
+  const int n = g.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.y;
+
+  float* bias = reinterpret_cast<float*>(smem);
+  uint8_t* wbase = smem + L::kBiasBytes + warp * L::kPerWarp;
+  uint8_t* sQ = wbase;
+  uint8_t* sK = sQ + L::kTileBytes;
+  uint8_t* sV = sK + L::kTileBytes;
+  int* s_tok = reinterpret_cast<int*>(sV + L::kTileBytes);
+  int* s_reg = s_tok + 64;
+
+  // ---- per-CTA: expand relative_position_bias_table[index[i, j], h] * log2e into the bias tile
+  for (int e = tid; e < 64 * 64; e += kWarps * 32) {
+    const int i = e >> 6, j = e & 63;
+    float v = 0.f;
+    if (j >= n) {
+      v = -INFINITY;
+    } else if (i < n) {
+      int rt, ct, rt2, ct2;
+      relpos_terms(g, i, rt, ct);
+      relpos_terms(g, j, rt2, ct2);
+      v = p.table[static_cast<int64_t>(rt - ct2) * p.H + h] * kLog2e;
+    }
+    bias[i * kBiasStride + j] = v;
+  }
+  __syncthreads();
+
+  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  const int gq = lane >> 2, qq = lane & 3;
+  const float mask_log2 = -100.0f * kLog2e;
+  const int n_qt = (n + 15) / 16;
+  const int units = p.B * g.nW;
+
+  for (int u = blockIdx.x * kWarps + warp; u < units; u += gridDim.x * kWarps) {
+    const int b = u / g.nW, w = u % g.nW;
+    // ---- window metadata: two slots per lane
+    int first_reg = 0;
+    bool differs = false;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int s = lane + rep * 32;
+      int tok = -2, reg = -1;
+      if (s < n) slot_lookup(g, w, s, tok, reg);
+      s_tok[s] = tok;
+      s_reg[s] = reg;
+      if (rep == 0) first_reg = __shfl_sync(0xffffffffu, reg, 0);
+      differs = differs || (s < n && reg != first_reg);
+    }
+    const bool has_mask = __any_sync(0xffffffffu, differs);
+    __syncwarp();
+
+    // ---- gather q, k, v rows of this (window, head): 16-byte chunks, pad tokens take the qkv bias
+    {
+      const int64_t tok_base = static_cast<int64_t>(b) * g.T;
+#pragma unroll 4
+      for (int e = lane; e < 3 * 64 * kChunks; e += 32) {
+        const int sel = e / (64 * kChunks);
+        const int r = (e / kChunks) & 63, c = e % kChunks;
+        const int t = s_tok[r];
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0) {
+          val = *reinterpret_cast<const uint4*>(p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8);
+        } else if (t == -1 && p.qkv_bias != nullptr) {
+          const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+          val.x = pack2_bf16(bsrc[0], bsrc[1]);
+          val.y = pack2_bf16(bsrc[2], bsrc[3]);
+          val.z = pack2_bf16(bsrc[4], bsrc[5]);
+          val.w = pack2_bf16(bsrc[6], bsrc[7]);
+        }
+        *reinterpret_cast<uint4*>(wbase + sel * L::kTileBytes + r * kStride + c * 16) = val;
+      }
+    }
+    __syncwarp();
+
+    // ---- K^T and V fragments for the whole window, kept in registers across the query tiles
+    uint32_t kf[8][D / 16][2], vf[4][D / 8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) load_b_frag_nt<kStride>(kf[nt][kk][0], kf[nt][kk][1], k_base, nt * 8, kk * 16, lane);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) load_b_frag_t<kStride>(vf[kb][nd][0], vf[kb][nd][1], v_base, kb * 16, nd * 8, lane);
+
+    for (int qt = 0; qt < n_qt; ++qt) {
+      const int row0 = qt * 16;
+      uint32_t aq[D / 16][4];
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) load_a_frag<kStride>(aq[kk], q_base, row0, kk * 16, lane);
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) mma_bf16_16816(s[nt], aq[kk], kf[nt][kk][0], kf[nt][kk][1]);
+      }
+      const int i0 = row0 + gq, i1 = i0 + 8;
+      const float* b0p = bias + i0 * kBiasStride + qq * 2;
+      const float* b1p = bias + i1 * kBiasStride + qq * 2;
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 bb0 = *reinterpret_cast<const float2*>(b0p + nt * 8);
+        const float2 bb1 = *reinterpret_cast<const float2*>(b1p + nt * 8);
+        s[nt][0] = fmaf(s[nt][0], p.scale_log2, bb0.x);
+        s[nt][1] = fmaf(s[nt][1], p.scale_log2, bb0.y);
+        s[nt][2] = fmaf(s[nt][2], p.scale_log2, bb1.x);
+        s[nt][3] = fmaf(s[nt][3], p.scale_log2, bb1.y);
+      }
+      if (has_mask) {
+        const int rg0 = s_reg[i0], rg1 = s_reg[i1];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int2 rj = *reinterpret_cast<const int2*>(s_reg + nt * 8 + qq * 2);
+          if (rj.x >= 0) {   // real window slots only (-1 marks the tile padding, already -inf through the bias)
+            if (rg0 != rj.x) s[nt][0] += mask_log2;
+            if (rg1 != rj.x) s[nt][2] += mask_log2;
+          }
+          if (rj.y >= 0) {
+            if (rg0 != rj.y) s[nt][1] += mask_log2;
+            if (rg1 != rj.y) s[nt][3] += mask_log2;
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = ex2f(s[nt][0] - m0); s[nt][1] = ex2f(s[nt][1] - m0);
+        s[nt][2] = ex2f(s[nt][2] - m1); s[nt][3] = ex2f(s[nt][3] - m1);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      float oacc[D / 8][4];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        uint32_t ap[4];
+        ap[0] = pack2_bf16(s[2 * kb][0], s[2 * kb][1]);
+        ap[1] = pack2_bf16(s[2 * kb][2], s[2 * kb][3]);
+        ap[2] = pack2_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+        ap[3] = pack2_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) mma_bf16_16816(oacc[nd], ap, vf[kb][nd][0], vf[kb][nd][1]);
+      }
+      const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+      // stage the 16 x D output tile in this tile's (already consumed) Q rows, then 16-byte scatter stores
+      __syncwarp();
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) {
+        *reinterpret_cast<uint32_t*>(sQ + i0 * kStride + (nd * 8 + qq * 2) * 2) = pack2_bf16(oacc[nd][0] * inv0, oacc[nd][1] * inv0);
+        *reinterpret_cast<uint32_t*>(sQ + i1 * kStride + (nd * 8 + qq * 2) * 2) = pack2_bf16(oacc[nd][2] * inv1, oacc[nd][3] * inv1);
+      }
+      const int t0 = s_tok[i0], t1 = s_tok[i1];
+      if (qq == 0) {
+        if (t0 >= 0) p.lse2[(static_cast<int64_t>(b) * g.T + t0) * p.H + h] = m0 + log2f(l0);
+        if (t1 >= 0) p.lse2[(static_cast<int64_t>(b) * g.T + t1) * p.H + h] = m1 + log2f(l1);
+      }
+      __syncwarp();
+      for (int e = lane; e < 16 * kChunks; e += 32) {
+        const int r = row0 + e / kChunks, c = e % kChunks;
+        const int t = s_tok[r];
+        if (t >= 0)
+          *reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * g.T + t) * p.C + h * D + c * 8) =
+              *reinterpret_cast<const uint4*>(sQ + r * kStride + c * 16);
+      }
+    }
+    __syncwarp();   // the next window overwrites this warp's tiles
+  }
+}
+
+template <int D>
+int launch_small(const WinParams& p, cudaStream_t stream) {
+  using L = SmallSmem<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(win_attn_fwd_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  const int units = p.B * p.g.nW;
+  const int ctas_per_sm = (227 * 1024) / (L::kTotal + 1024);
+  int grid_x = (148 * (ctas_per_sm > 0 ? ctas_per_sm : 1) + p.H - 1) / p.H;
+  const int max_x = (units + kWarps - 1) / kWarps;
+  if (grid_x > max_x) grid_x = max_x;
+  if (grid_x < 1) grid_x = 1;
+  win_attn_fwd_small_kernel<D><<<dim3(grid_x, p.H), kWarps * 32, L::kTotal, stream>>>(p);
+  return set_cuda_error(cudaGetLastError());
+}
+
+
+// =================================================================================================
+// Fused backward for small windows: dq, dk, dv, d(qkv.bias through pad tokens) and d(bias table) in ONE kernel.
+//   persistent CTA = (head, slice of the window list), 4 warps.
+//   phase 1 (warp = 16-row QUERY tile): S, P = exp2(S*c + bias + mask - lse2), dP = dO V^T, dS = P o (dP - D);
+//            dQ = dS K written out; dBias += dS kept in registers ACROSS windows; P, dS -> bf16 smem tiles
+//   phase 2 (warp = 16-row KEY tile):  dV = P^T dO, dK = dS^T Q with the A fragments read transposed from smem
+//   once per CTA: dBias registers -> atomicAdd into d(relative_position_bias_table).
+// No recomputation (5 GEMMs, one exp per logit) and one atomic per (i, j) per CTA instead of per window.
+// =================================================================================================
+template <int STRIDE_BYTES>
+__device__ __forceinline__ void load_a_frag_trans(uint32_t (&a)[4], uint32_t tile_base, int k0, int m0, int lane) {
+  // A[m][k] = X[k0 + k][m0 + m] for X stored row-major with k as the row index
+  const uint32_t addr = tile_base + (k0 + (lane & 7) + ((lane >> 4) & 1) * 8) * STRIDE_BYTES + (m0 + ((lane >> 3) & 1) * 8) * 2;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+}
+
+constexpr int kPStride = 144;   // bytes per row of the bf16 P / dS tiles (64 columns + 16 B pad)
+
+template <int D>
+struct SmallBwdSmem {
+  static constexpr int kStride = Tile<D>::kStride;
+  static constexpr int kTileBytes = 64 * kStride;
+  static constexpr int kPBytes = 64 * kPStride;
+  static constexpr int kTabFloats = 2200;   // >= prod(2*window-1) for every window with <= 64 tokens... checked on host
+  static constexpr int kTotal = 4 * kTileBytes + 2 * kPBytes + 2 * 64 * 4 /*lse, dsum*/ + 4 * 64 * 4 /*meta*/;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128, 3)
+win_attn_bwd_small_kernel(const WinParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  using L = SmallBwdSmem<D>;
+  constexpr int kStride = L::kStride;
+  constexpr int kChunks = D / 8;
+  const WinGeom& g = p.g;
+  const int n = g.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.y;
+
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + L::kTileBytes;
+  uint8_t* sV = sK + L::kTileBytes;
+  uint8_t* sDO = sV + L::kTileBytes;
+  uint8_t* sP = sDO + L::kTileBytes;
+  uint8_t* sDS = sP + L::kPBytes;
+  float* s_lse = reinterpret_cast<float*>(sDS + L::kPBytes);
+  float* s_dsum = s_lse + 64;
+  int* s_tok = reinterpret_cast<int*>(s_dsum + 64);
+  int* s_reg = s_tok + 64;
+  int* s_rt = s_reg + 64;
+  int* s_ct = s_rt + 64;
+  float* tab = reinterpret_cast<float*>(s_ct + 64);   // [tab_rows] bias table column of this head, x log2e
+
+  for (int t = tid; t < g.tab_rows; t += 128) tab[t] = p.table[static_cast<int64_t>(t) * p.H + h] * kLog2e;
+  if (tid < 64) {
+    int rt = g.tab_rows - 1, ct = 0;
+    if (tid < n) relpos_terms(g, tid, rt, ct);
+    s_rt[tid] = rt;
+    s_ct[tid] = ct;
+  }
+
+  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  const uint32_t do_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDO));
+  const uint32_t p_base = static_cast<uint32_t>(__cvta_generic_to_shared(sP));
+  const uint32_t ds_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDS));
+  const int gq = lane >> 2, qq = lane & 3;
+  const float mask_log2 = -100.0f * kLog2e;
+  const float scale = p.scale_log2 / kLog2e;
+  const int units = p.B * g.nW;
+  const int row0 = warp * 16;                       // this warp's query tile (phase 1) and key tile (phase 2)
+  const bool tile_live = row0 < n;
+
+  float dbias[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dbias[i][0] = dbias[i][1] = dbias[i][2] = dbias[i][3] = 0.f;
+  float pad_dk[D / 8][2], pad_dv[D / 8][2];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) pad_dk[i][0] = pad_dk[i][1] = pad_dv[i][0] = pad_dv[i][1] = 0.f;
+
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int b = u / g.nW, w = u % g.nW;
+    __syncthreads();                                // previous window fully consumed (and tab / terms written)
+    if (tid < 64) {
+      int tok = -2, reg = -1;
+      if (tid < n) slot_lookup(g, w, tid, tok, reg);
+      s_tok[tid] = tok;
+      s_reg[tid] = reg;
+      float l = INFINITY, d = 0.f;                  // pad / dead query rows: P = exp2(. - inf) = 0
+      if (tok >= 0) {
+        const int64_t idx = (static_cast<int64_t>(b) * g.T + tok) * p.H + h;
+        l = p.lse2[idx];
+        d = p.dsum[idx];
+      }
+      s_lse[tid] = l;
+      s_dsum[tid] = d;
+    }
+    __syncthreads();
+    {
+      const int64_t tok_base = static_cast<int64_t>(b) * g.T;
+#pragma unroll 4
+      for (int e = tid; e < 4 * 64 * kChunks; e += 128) {
+        const int sel = e / (64 * kChunks);          // 0 q, 1 k, 2 v, 3 dO
+        const int r = (e / kChunks) & 63, c = e % kChunks;
+        const int t = s_tok[r];
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0) {
+          const __nv_bfloat16* src = sel < 3 ? p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8
+                                             : p.d_out + (tok_base + t) * p.C + h * D + c * 8;
+          val = *reinterpret_cast<const uint4*>(src);
+        } else if (t == -1 && sel < 3 && p.qkv_bias != nullptr) {
+          const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+          val.x = pack2_bf16(bsrc[0], bsrc[1]);
+          val.y = pack2_bf16(bsrc[2], bsrc[3]);
+          val.z = pack2_bf16(bsrc[4], bsrc[5]);
+          val.w = pack2_bf16(bsrc[6], bsrc[7]);
+        }
+        *reinterpret_cast<uint4*>(smem + sel * L::kTileBytes + r * kStride + c * 16) = val;
+      }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ phase 1: this warp's query tile
+    if (tile_live) {
+      uint32_t aq[D / 16][4], ado[D / 16][4];
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        load_a_frag<kStride>(aq[kk], q_base, row0, kk * 16, lane);
+        load_a_frag<kStride>(ado[kk], do_base, row0, kk * 16, lane);
+      }
+      const int i0 = row0 + gq, i1 = i0 + 8;
+      const float lse0 = s_lse[i0], lse1 = s_lse[i1], ds0 = s_dsum[i0], ds1 = s_dsum[i1];
+      const int rt0 = s_rt[i0], rt1 = s_rt[i1], rg0 = s_reg[i0], rg1 = s_reg[i1];
+      float dq[D / 8][4];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {        // 32 keys per step
+        float s[4][4], dp[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+          dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            uint32_t b0, b1;
+            load_b_frag_nt<kStride>(b0, b1, k_base, half * 32 + nt * 8, kk * 16, lane);
+            mma_bf16_16816(s[nt], aq[kk], b0, b1);
+            load_b_frag_nt<kStride>(b0, b1, v_base, half * 32 + nt * 8, kk * 16, lane);
+            mma_bf16_16816(dp[nt], ado[kk], b0, b1);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          float pv[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = half * 32 + nt * 8 + qq * 2 + e;
+            float p0 = 0.f, p1 = 0.f;
+            if (j < n) {
+              const int ct = s_ct[j], rj = s_reg[j];
+              p0 = ex2f(fmaf(s[nt][e], p.scale_log2, tab[rt0 - ct]) + (rg0 != rj ? mask_log2 : 0.f) - lse0);
+              p1 = ex2f(fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - ct]) + (rg1 != rj ? mask_log2 : 0.f) - lse1);
+            }
+            pv[e] = p0;
+            pv[2 + e] = p1;
+            dp[nt][e] = p0 * (dp[nt][e] - ds0);
+            dp[nt][2 + e] = p1 * (dp[nt][2 + e] - ds1);
+            dbias[half * 4 + nt][e] += dp[nt][e];
+            dbias[half * 4 + nt][2 + e] += dp[nt][2 + e];
+          }
+          const int col = (half * 32 + nt * 8 + qq * 2) * 2;
+          *reinterpret_cast<uint32_t*>(sP + i0 * kPStride + col) = pack2_bf16(pv[0], pv[1]);
+          *reinterpret_cast<uint32_t*>(sP + i1 * kPStride + col) = pack2_bf16(pv[2], pv[3]);
+          *reinterpret_cast<uint32_t*>(sDS + i0 * kPStride + col) = pack2_bf16(dp[nt][0], dp[nt][1]);
+          *reinterpret_cast<uint32_t*>(sDS + i1 * kPStride + col) = pack2_bf16(dp[nt][2], dp[nt][3]);
+        }
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          uint32_t ads[4];
+          ads[0] = pack2_bf16(dp[2 * kb][0], dp[2 * kb][1]);
+          ads[1] = pack2_bf16(dp[2 * kb][2], dp[2 * kb][3]);
+          ads[2] = pack2_bf16(dp[2 * kb + 1][0], dp[2 * kb + 1][1]);
+          ads[3] = pack2_bf16(dp[2 * kb + 1][2], dp[2 * kb + 1][3]);
+#pragma unroll
+          for (int nd = 0; nd < D / 8; ++nd) {
+            uint32_t b0, b1;
+            load_b_frag_t<kStride>(b0, b1, k_base, half * 32 + kb * 16, nd * 8, lane);
+            mma_bf16_16816(dq[nd], ads, b0, b1);
+          }
+        }
+      }
+      const int t0 = s_tok[i0], t1 = s_tok[i1];
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) {
+        const int col = h * D + nd * 8 + qq * 2;
+        if (t0 >= 0)
+          *reinterpret_cast<uint32_t*>(p.dqkv + (static_cast<int64_t>(b) * g.T + t0) * 3 * p.C + col) =
+              pack2_bf16(dq[nd][0] * scale, dq[nd][1] * scale);
+        if (t1 >= 0)
+          *reinterpret_cast<uint32_t*>(p.dqkv + (static_cast<int64_t>(b) * g.T + t1) * 3 * p.C + col) =
+              pack2_bf16(dq[nd][2] * scale, dq[nd][3] * scale);
+      }
+    } else {
+      // dead query tile (all slots beyond the window): its P / dS rows must read as zero in phase 2
+      for (int e = lane; e < 16 * (kPStride / 4); e += 32) {
+        reinterpret_cast<uint32_t*>(sP + row0 * kPStride)[e] = 0u;
+        reinterpret_cast<uint32_t*>(sDS + row0 * kPStride)[e] = 0u;
+      }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ phase 2: this warp's key tile
+    if (tile_live) {
+      float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+      }
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {              // 16 queries per k-step
+        uint32_t apt[4], adst[4];
+        load_a_frag_trans<kPStride>(apt, p_base, kb * 16, row0, lane);
+        load_a_frag_trans<kPStride>(adst, ds_base, kb * 16, row0, lane);
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) {
+          uint32_t b0, b1;
+          load_b_frag_t<kStride>(b0, b1, do_base, kb * 16, nd * 8, lane);
+          mma_bf16_16816(dv[nd], apt, b0, b1);
+          load_b_frag_t<kStride>(b0, b1, q_base, kb * 16, nd * 8, lane);
+          mma_bf16_16816(dk[nd], adst, b0, b1);
+        }
+      }
+      const int j0 = row0 + gq, j1 = j0 + 8;
+      const int t0 = s_tok[j0], t1 = s_tok[j1];
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) {
+        const int col = h * D + nd * 8 + qq * 2;
+        if (t0 >= 0) {
+          const int64_t base = (static_cast<int64_t>(b) * g.T + t0) * 3 * p.C;
+          *reinterpret_cast<uint32_t*>(p.dqkv + base + p.C + col) = pack2_bf16(dk[nd][0] * scale, dk[nd][1] * scale);
+          *reinterpret_cast<uint32_t*>(p.dqkv + base + 2 * p.C + col) = pack2_bf16(dv[nd][0], dv[nd][1]);
+        } else if (t0 == -1) {
+          pad_dk[nd][0] += dk[nd][0] * scale; pad_dk[nd][1] += dk[nd][1] * scale;
+          pad_dv[nd][0] += dv[nd][0]; pad_dv[nd][1] += dv[nd][1];
+        }
+        if (t1 >= 0) {
+          const int64_t base = (static_cast<int64_t>(b) * g.T + t1) * 3 * p.C;
+          *reinterpret_cast<uint32_t*>(p.dqkv + base + p.C + col) = pack2_bf16(dk[nd][2] * scale, dk[nd][3] * scale);
+          *reinterpret_cast<uint32_t*>(p.dqkv + base + 2 * p.C + col) = pack2_bf16(dv[nd][2], dv[nd][3]);
+        } else if (t1 == -1) {
+          pad_dk[nd][0] += dk[nd][2] * scale; pad_dk[nd][1] += dk[nd][3] * scale;
+          pad_dv[nd][0] += dv[nd][2]; pad_dv[nd][1] += dv[nd][3];
+        }
+      }
+    }
+  }
+
+  // ---- once per CTA: bias-table gradient and the pad-token share of d(qkv.bias)
+  if (p.dtable != nullptr && tile_live) {
+    const int i0 = row0 + gq, i1 = i0 + 8;
+    const int rt0 = s_rt[i0 < 64 ? i0 : 63], rt1 = s_rt[i1 < 64 ? i1 : 63];
+#pragma unroll
+    for (int t8 = 0; t8 < 8; ++t8) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = t8 * 8 + qq * 2 + e;
+        if (j >= n) continue;
+        const int ct = s_ct[j];
+        if (i0 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt0 - ct) * p.H + h, dbias[t8][e]);
+        if (i1 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt1 - ct) * p.H + h, dbias[t8][2 + e]);
+      }
+    }
+  }
+  if (p.dbias_pad != nullptr && g.n * g.nW != g.T) {
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = pad_dk[nd][e], c = pad_dv[nd][e];
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, off);
+          c += __shfl_xor_sync(0xffffffffu, c, off);
+        }
+        if (gq == 0) {
+          const int col = h * D + nd * 8 + qq * 2 + e;
+          if (a != 0.f) atomicAdd(p.dbias_pad + p.C + col, a);
+          if (c != 0.f) atomicAdd(p.dbias_pad + 2 * p.C + col, c);
+        }
+      }
+    }
+  }
+}
+
+template <int D>
+int launch_small_bwd(const WinParams& p, cudaStream_t stream) {
+  using L = SmallBwdSmem<D>;
+  const size_t smem = L::kTotal + static_cast<size_t>(round_up(p.g.tab_rows, 4)) * 4;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(win_attn_bwd_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_bytes = smem;
+  }
+  const int units = p.B * p.g.nW;
+  int ctas_per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  if (ctas_per_sm > 3) ctas_per_sm = 3;             // register-limited (launch bounds)
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int grid_x = (2 * 148 * ctas_per_sm + p.H - 1) / p.H;   // ~2 waves of persistent CTAs per head slice
+  if (grid_x > units) grid_x = units;
+  if (grid_x < 1) grid_x = 1;
+  win_attn_bwd_small_kernel<D><<<dim3(grid_x, p.H), 128, smem, stream>>>(p);
+  return set_cuda_error(cudaGetLastError());
+}
+
+}  // namespace
+
+int win_attn_fwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream) {
+  return head_dim == 16 ? launch_small<16>(p, stream) : launch_small<32>(p, stream);
+}
+
+int win_attn_bwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream) {
+  return head_dim == 16 ? launch_small_bwd<16>(p, stream) : launch_small_bwd<32>(p, stream);
+}
+
+}  // namespace lcbi

@@ -85,6 +85,38 @@ __device__ __forceinline__ void relpos_terms(const WinGeom& g, int s, int& row_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// kernel parameters shared by window_attn.cu and window_attn_small.cu
+// ---------------------------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kKeyChunk = 64;
+
+struct WinParams {
+  WinGeom g;
+  int B, H, C;
+  float scale_log2;             // head_dim^-0.5 * log2(e)
+  const __nv_bfloat16* qkv;     // (B, T, 3, H, D)
+  const float* qkv_bias;        // (3*C) or nullptr
+  const float* table;           // (tab_rows, H)
+  __nv_bfloat16* out;           // (B, T, C)                      [fwd]
+  float* lse2;                  // (B, T, H) log2-domain logsumexp [fwd out / bwd in]
+  // backward
+  const __nv_bfloat16* d_out;   // (B, T, C)
+  const float* dsum;            // (B, T, H) rowsum(dO o O)
+  __nv_bfloat16* dqkv;          // (B, T, 3, H, D)
+  float* dbias_pad;             // (3*C) fp32, += gradient reaching qkv.bias through the pad tokens
+  float* dtable;                // (tab_rows, H) fp32, +=
+  int win_splits;               // dq kernel: number of window subsets
+};
+
+template <int D>
+struct Tile {
+  static constexpr int kStride = D * 2 + 16;   // bytes per smem row: +16 keeps ldmatrix conflict-free
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+
+// ---------------------------------------------------------------------------------------------
 // warp-level MMA helpers (m16n8k16, bf16 x bf16 -> fp32)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
