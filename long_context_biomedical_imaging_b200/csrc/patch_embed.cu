@@ -59,25 +59,26 @@ patch_embed_fwd_kernel(const TIn* __restrict__ img, const float* __restrict__ w,
   float acc[4][4] = {};
 
   for (int k0 = 0; k0 < g.K; k0 += KC) {
+    const int kmax = min(KC, g.K - k0);       // only the real reduction extent is staged (K is 4..16 for the
+                                              // long-context configs: filling all KC rows would be mostly waste)
     // A tile: element e -> (kk = e / TM, mm = e % TM); consecutive threads walk adjacent patches
-    for (int e = tid; e < TM * KC; e += kThreads) {
+    for (int e = tid; e < TM * kmax; e += kThreads) {
       const int kk = e / TM, mm = e % TM;
       float v = 0.f;
-      if (k0 + kk < g.K && m0 + mm < g.M) {
+      if (m0 + mm < g.M) {
         const int64_t off = px_offset(g, m0 + mm, k0 + kk);
         if (off >= 0) v = load_px(img + off);
       }
       As[kk][mm] = v;
     }
     // W tile (transposed on the fly): W[n][k] -> Ws[k][n]; consecutive threads walk k (contiguous in W)
-    for (int e = tid; e < TN * KC; e += kThreads) {
-      const int kk = e % KC, nn = e / KC;
+    for (int e = tid; e < TN * kmax; e += kThreads) {
+      const int kk = e % kmax, nn = e / kmax;
       float v = 0.f;
-      if (k0 + kk < g.K && n0 + nn < g.N) v = w[static_cast<int64_t>(n0 + nn) * g.K + k0 + kk];
+      if (n0 + nn < g.N) v = w[static_cast<int64_t>(n0 + nn) * g.K + k0 + kk];
       Ws[kk][nn] = v;
     }
     __syncthreads();
-    const int kmax = min(KC, g.K - k0);
     for (int kk = 0; kk < kmax; ++kk) {
       const float4 b4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
       const float a0 = As[kk][ty * 4 + 0], a1 = As[kk][ty * 4 + 1], a2 = As[kk][ty * 4 + 2], a3 = As[kk][ty * 4 + 3];
@@ -232,6 +233,117 @@ __global__ void patch_embed_bwd_x_kernel(const TG* __restrict__ dout, const floa
   dimg[idx] = s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small-K backward (K <= 16): one pass over dOut produces dW, dbias and (when the batch is 1, so that the sum over
+// the batch is the identity) dpos. CTA = kBwRows patches x 128 channels; thread = 4 channels; warp w takes rows
+// w, w+8, ... of the slab. The slab's pixels are staged once in shared memory ([row][k], K floats per row), every
+// dOut row is read with one coalesced 16-byte load per thread, partial dW[K][4] / dbias[4] live in registers and
+// are reduced across the 8 warps through shared memory, then added to global with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwRows = 256;
+constexpr int kBwKMax = 16;
+
+template <typename TIn, typename TG>
+__global__ void __launch_bounds__(256)
+patch_embed_bwd_smallk_kernel(const TIn* __restrict__ img, const TG* __restrict__ dout, float* __restrict__ dw,
+                              float* __restrict__ dbias, float* __restrict__ dpos_copy, PEGeom g) {
+  extern __shared__ __align__(16) float pe_smem[];
+  float (*px)[kBwKMax + 1] = reinterpret_cast<float (*)[kBwKMax + 1]>(pe_smem);           // [kBwRows][17]
+  float* red = pe_smem + kBwRows * (kBwKMax + 1);                                          // [8][K+1][132]
+  const int red_k = 132, red_w = (g.K + 1) * 132;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.y * 128 + lane * 4;
+  const bool live = n < g.N;                 // N is a multiple of 4 on this path (checked by the launcher)
+  float acc[kBwKMax][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < kBwKMax; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  const int64_t n_slabs = (g.M + kBwRows - 1) / kBwRows;
+  // persistent over the row slabs: the partial sums stay in registers, so each CTA issues its atomics once
+  for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+    const int64_t m_begin = slab * kBwRows;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(kBwRows), g.M - m_begin));
+    __syncthreads();                         // previous slab's pixels fully consumed
+    for (int e = tid; e < rows * g.K; e += 256) {
+      const int r = e / g.K, k = e % g.K;
+      const int64_t off = px_offset(g, m_begin + r, k);
+      px[r][k] = off >= 0 ? load_px(img + off) : 0.f;
+    }
+    __syncthreads();
+    if (live) {
+      auto load_row = [&](int r) {
+        const TG* src = dout + (m_begin + r) * g.N + n;
+        if constexpr (sizeof(TG) == 4) {
+          return *reinterpret_cast<const float4*>(src);
+        } else {
+          const uint2 raw = *reinterpret_cast<const uint2*>(src);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          return make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+      };
+      auto use_row = [&](int r, const float4& gv) {
+        if (dpos_copy != nullptr) *reinterpret_cast<float4*>(dpos_copy + (m_begin + r) * g.N + n) = gv;
+        bsum[0] += gv.x; bsum[1] += gv.y; bsum[2] += gv.z; bsum[3] += gv.w;
+#pragma unroll
+        for (int k = 0; k < kBwKMax; ++k) {
+          if (k < g.K) {
+            const float a = px[r][k];
+            acc[k][0] = fmaf(a, gv.x, acc[k][0]); acc[k][1] = fmaf(a, gv.y, acc[k][1]);
+            acc[k][2] = fmaf(a, gv.z, acc[k][2]); acc[k][3] = fmaf(a, gv.w, acc[k][3]);
+          }
+        }
+      };
+      int r = warp;
+      for (; r + 24 < rows; r += 32) {       // four rows in flight per thread
+        const float4 g0 = load_row(r), g1 = load_row(r + 8), g2 = load_row(r + 16), g3 = load_row(r + 24);
+        use_row(r, g0); use_row(r + 8, g1); use_row(r + 16, g2); use_row(r + 24, g3);
+      }
+      for (; r < rows; r += 8) use_row(r, load_row(r));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kBwKMax; ++k)
+    if (k < g.K)
+      *reinterpret_cast<float4*>(red + warp * red_w + k * red_k + lane * 4) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+  *reinterpret_cast<float4*>(red + warp * red_w + g.K * red_k + lane * 4) = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+  __syncthreads();
+  for (int e = tid; e < (g.K + 1) * 128; e += 256) {
+    const int k = e / 128, c = e % 128;
+    const int col = blockIdx.y * 128 + c;
+    if (col >= g.N) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * red_w + k * red_k + c];
+    if (k == g.K) {
+      if (dbias != nullptr) atomicAdd(&dbias[col], sum);
+    } else {
+      atomicAdd(&dw[static_cast<int64_t>(col) * g.K + k], sum);
+    }
+  }
+}
+
+// dpos[p][n] = sum_b dOut[b][p][n], four channels per thread
+template <typename TG>
+__global__ void patch_embed_bwd_pos4_kernel(const TG* __restrict__ dout, float* __restrict__ dpos, int B, int64_t np_n4) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= np_n4) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const TG* src = dout + (b * np_n4 + idx) * 4;
+    if constexpr (sizeof(TG) == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    } else {
+      const uint2 raw = *reinterpret_cast<const uint2*>(src);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      s.x += lo.x; s.y += lo.y; s.z += hi.x; s.w += hi.y;
+    }
+  }
+  *reinterpret_cast<float4*>(dpos + idx * 4) = s;
+}
+
 int fill_geom(PEGeom& g, const int* img_dims, const int* patch, const int* grid, int B, int Cin, int N) {
   if (B <= 0 || Cin <= 0 || N <= 0) return LCBI_ERR_BAD_ARG;
   for (int i = 0; i < 3; ++i)
@@ -278,26 +390,64 @@ int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, con
     e = cudaMemsetAsync(dbias, 0, sizeof(float) * N, stream);
     if (e != cudaSuccess) return set_cuda_error(e);
   }
-  dim3 grd(static_cast<unsigned>((g.M + MS - 1) / MS), (N + TN - 1) / TN, (g.K + KC - 1) / KC);
+  const int64_t np = static_cast<int64_t>(g.Gd) * g.Gh * g.Gw;
+  bool dpos_done = false;
+  if (g.K <= kBwKMax && (N & 3) == 0) {
+    // single pass over dOut; with B == 1 the position-embedding gradient is a cast/copy of dOut and rides along
+    float* dpos_copy = (dpos != nullptr && B == 1) ? dpos : nullptr;
+    dpos_done = dpos_copy != nullptr;
+    const int col_blocks = (N + 127) / 128;
+    int64_t slabs = (g.M + kBwRows - 1) / kBwRows;
+    // ~6 persistent CTAs per SM in total for latency hiding, but never more than 2*148 CTAs adding into the same
+    // dW/dbias addresses (measured: atomic contention dominates the narrow-N Swin cases beyond that)
+    int64_t want = (6 * 148 + col_blocks - 1) / col_blocks;
+    if (want > 2 * 148) want = 2 * 148;
+    dim3 sg(static_cast<unsigned>(slabs < want ? slabs : want), col_blocks);
+    const size_t sk_smem = (static_cast<size_t>(kBwRows) * (kBwKMax + 1) + static_cast<size_t>(8) * (g.K + 1) * 132) * 4;
+#define LCBI_PE_BSK(TI, TG)                                                                                      \
+  do {                                                                                                           \
+    if (sk_smem > 48 * 1024)                                                                                     \
+      cudaFuncSetAttribute(patch_embed_bwd_smallk_kernel<TI, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           static_cast<int>(sk_smem));                                                           \
+    patch_embed_bwd_smallk_kernel<TI, TG><<<sg, 256, sk_smem, stream>>>(                                         \
+        static_cast<const TI*>(img), static_cast<const TG*>(dout), dw, dbias, dpos_copy, g);                     \
+  } while (0)
+    if (img_is_bf16) {
+      if (dout_is_bf16) LCBI_PE_BSK(__nv_bfloat16, __nv_bfloat16); else LCBI_PE_BSK(__nv_bfloat16, float);
+    } else {
+      if (dout_is_bf16) LCBI_PE_BSK(float, __nv_bfloat16); else LCBI_PE_BSK(float, float);
+    }
+#undef LCBI_PE_BSK
+  } else {
+    dim3 grd(static_cast<unsigned>((g.M + MS - 1) / MS), (N + TN - 1) / TN, (g.K + KC - 1) / KC);
 #define LCBI_PE_BWD(TI, TG) \
   patch_embed_bwd_w_kernel<TI, TG><<<grd, kThreads, 0, stream>>>(static_cast<const TI*>(img), \
                                                                 static_cast<const TG*>(dout), dw, dbias, g)
-  if (img_is_bf16) {
-    if (dout_is_bf16) LCBI_PE_BWD(__nv_bfloat16, __nv_bfloat16); else LCBI_PE_BWD(__nv_bfloat16, float);
-  } else {
-    if (dout_is_bf16) LCBI_PE_BWD(float, __nv_bfloat16); else LCBI_PE_BWD(float, float);
-  }
+    if (img_is_bf16) {
+      if (dout_is_bf16) LCBI_PE_BWD(__nv_bfloat16, __nv_bfloat16); else LCBI_PE_BWD(__nv_bfloat16, float);
+    } else {
+      if (dout_is_bf16) LCBI_PE_BWD(float, __nv_bfloat16); else LCBI_PE_BWD(float, float);
+    }
 #undef LCBI_PE_BWD
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);
-  const int64_t np = static_cast<int64_t>(g.Gd) * g.Gh * g.Gw;
-  if (dpos) {
-    const int64_t total = np * N;
-    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-    if (dout_is_bf16)
-      patch_embed_bwd_pos_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout), dpos, B, np, N);
-    else
-      patch_embed_bwd_pos_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(dout), dpos, B, np, N);
+  if (dpos && !dpos_done) {
+    if ((N & 3) == 0) {
+      const int64_t total4 = np * N / 4;
+      const unsigned blocks = static_cast<unsigned>((total4 + 255) / 256);
+      if (dout_is_bf16)
+        patch_embed_bwd_pos4_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout), dpos, B, total4);
+      else
+        patch_embed_bwd_pos4_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(dout), dpos, B, total4);
+    } else {
+      const int64_t total = np * N;
+      const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+      if (dout_is_bf16)
+        patch_embed_bwd_pos_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout), dpos, B, np, N);
+      else
+        patch_embed_bwd_pos_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(dout), dpos, B, np, N);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
   }
