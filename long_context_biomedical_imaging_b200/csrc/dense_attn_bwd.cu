@@ -43,12 +43,28 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kStep = 64;                          // queries per pipeline step
 constexpr int kStepBytes = kStep * kHeadDim * 2;   // 8 KB
 constexpr int kQStages = 4;
+// Per-query row terms ride along as one extra K=16 step of the S^T / dP^T GEMMs: the fp32 value is split into three
+// bf16 parts (hi, mid, lo) stored in columns 0-2 of a [64 queries x 16] K-major tile, multiplied by a constant
+// [128 keys x 16] tile holding (1, 1, 1, 0, ...). Tiles use the un-swizzled canonical layout: 8-row x 16-byte core
+// matrices, the two 16-byte k-halves of a row group 128 bytes apart (LBO), row groups 256 bytes apart (SBO).
+constexpr int kAugBytes = kStep * 16 * 2;          // 2 KB
+constexpr uint32_t kAugLbo = 128, kAugSbo = 256;
+__host__ __device__ constexpr int aug_chunk_offset(int row, int khalf) {   // byte offset of a 16-byte chunk
+  return (row >> 3) * static_cast<int>(kAugSbo) + khalf * static_cast<int>(kAugLbo) + (row & 7) * 16;
+}
 
 // TMEM columns: S^T and dP^T are double-buffered per 64-query step; the bf16 P^T / dS^T of a step overwrite, in
 // place, the first half of the columns their owner thread read (thread (row, hh) owns columns [32hh, 32hh+32) of a
 // buffer and writes 16 packed columns at [32hh, 32hh+16)); K and V sit in TMEM as the A operands of S^T / dP^T.
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemK = 448, kTmemV = 480;
-constexpr bool kDrainWithRed = false;   // dQ partials: red.global.add.v4.f32 from registers (no smem staging)
+constexpr bool kDrainWithRed = false;
+// Timing-only ablations (results become wrong; every barrier still fires): bit 0 no exp2, bit 1 no dQ GEMM/drain,
+// bit 2 no dS^T smem store, bit 3 drain without staging/TMA reduce, bit 4 compute warps only wait and arrive,
+// bit 5 no dV/dK GEMMs, bit 6 no extra (row-term) k-steps, bit 7 no S^T/dP^T GEMMs.
+#ifndef LCBI_BWD_ABLATE
+#define LCBI_BWD_ABLATE 0
+#endif
+constexpr int kAblate = LCBI_BWD_ABLATE;   // dQ partials: red.global.add.v4.f32 from registers (no smem staging)
 
 struct __align__(1024) BwdSmem {
   uint8_t k[kTileBytes];
@@ -57,8 +73,9 @@ struct __align__(1024) BwdSmem {
   uint8_t dout[kQStages][kStepBytes];   // likewise dV staging
   uint8_t ds[2][2 * kTileBytes];        // dS^T per 128-query tile (double-buffered): two [128 keys x 64 queries] atoms
   uint8_t dq_stage[2 * kTileBytes];     // two [128 queries x 32 fp32] SW128 tiles
-  float lse2[kQStages][kStep];
-  float dsum[kQStages][kStep];
+  uint8_t lse_aug[kQStages][kAugBytes];   // per-query -lse/scale as the B operand of one extra k-step of S^T
+  uint8_t d_aug[kQStages][kAugBytes];     // per-query -D likewise for dP^T
+  uint8_t ones[2 * kAugBytes];            // [128 keys x 16] constant A operand of those k-steps: (1, 1, 1, 0, ...)
   uint64_t kv_full;
   uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
   uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full;
@@ -78,17 +95,11 @@ __device__ long long* g_bwd_trace = nullptr;
 #define LCBI_TR(role, step, ev) do { } while (0)
 #endif
 
-__device__ __forceinline__ float4 lds128(const float* p) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
-  return v;
-}
-
 struct BwdParams {
   int B, H, Nq, Nk, Nq_pad;
   float scale, scale_log2;
-  const float* lse2;   // (B,H,Nq_pad)
-  const float* dsum;   // (B,H,Nq_pad)
+  const __nv_bfloat16* lse_aug;   // (B,H,Nq_pad/64) tiles of kAugBytes: -lse/scale split into bf16 (hi, mid, lo)
+  const __nv_bfloat16* d_aug;     // likewise -D, D = rowsum(dO o O)
   float* dq_acc;       // fp32 (B,Nq,H,64) accumulator
   int accumulate_dkv;
 };
@@ -118,12 +129,26 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// prep: D = rowsum(dO o O), lse2 = lse * log2e; 8 threads per (b, h, row)
+// prep: per query row the two terms the main kernel adds through its extra k-step, a = -lse/scale and b = -D with
+// D = rowsum(dO o O), each split into three bf16 parts and written in the operand tile layout; 8 threads per row
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 split3_bf16(float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  uint4 v;
+  v.x = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(mid)) << 16);
+  v.y = static_cast<uint32_t>(__bfloat16_as_ushort(lo));
+  v.z = 0u;
+  v.w = 0u;
+  return v;
+}
+
 __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
-                                const float* __restrict__ lse, float* __restrict__ lse2, float* __restrict__ dsum,
-                                int B, int H, int Nq, int Nq_pad, int64_t o_sb, int64_t o_sr, int64_t o_sh,
-                                int64_t do_sb, int64_t do_sr, int64_t do_sh) {
+                                const float* __restrict__ lse, uint8_t* __restrict__ lse_aug,
+                                uint8_t* __restrict__ d_aug, float inv_scale, int B, int H, int Nq, int Nq_pad,
+                                int64_t o_sb, int64_t o_sr, int64_t o_sh, int64_t do_sb, int64_t do_sr, int64_t do_sh) {
   // 8 threads per (b, h, row): each loads 16 bytes of O and dO; rows ordered (b, row, h) so that a warp's four
   // rows are adjacent heads of one token (contiguous 512 bytes in the usual (B,N,H,d) layout)
   const int sub = threadIdx.x & 7;
@@ -133,31 +158,32 @@ __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_
   const int h = static_cast<int>(r % H);
   const int row = static_cast<int>((r / H) % Nq_pad);
   const int b = static_cast<int>(r / (static_cast<int64_t>(H) * Nq_pad));
-  const int64_t out_idx = (static_cast<int64_t>(b) * H + h) * Nq_pad + row;
-  if (row >= Nq) {
-    if (sub == 0) {
-      lse2[out_idx] = INFINITY;   // exp2(x - inf) = 0: padded query columns contribute nothing
-      dsum[out_idx] = 0.f;
-    }
-    return;
-  }
-  const uint4 ov = *reinterpret_cast<const uint4*>(o + b * o_sb + row * o_sr + h * o_sh + sub * 8);
-  const uint4 dv = *reinterpret_cast<const uint4*>(d_o + b * do_sb + row * do_sr + h * do_sh + sub * 8);
-  const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-  const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+  const int64_t tile = (static_cast<int64_t>(b) * H + h) * (Nq_pad / kStep) + row / kStep;
+  const int64_t chunk0 = tile * kAugBytes + aug_chunk_offset(row % kStep, 0);
   float acc = 0.f;
+  if (row < Nq) {
+    const uint4 ov = *reinterpret_cast<const uint4*>(o + b * o_sb + row * o_sr + h * o_sh + sub * 8);
+    const uint4 dv = *reinterpret_cast<const uint4*>(d_o + b * do_sb + row * do_sr + h * do_sh + sub * 8);
+    const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+    const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 x = __bfloat1622float2(o2[i]), y = __bfloat1622float2(d2[i]);
-    acc = fmaf(x.x, y.x, acc);
-    acc = fmaf(x.y, y.y, acc);
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __bfloat1622float2(o2[i]), y = __bfloat1622float2(d2[i]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
   if (sub == 0) {
-    dsum[out_idx] = acc;
-    lse2[out_idx] = lse[(static_cast<int64_t>(b) * H + h) * Nq + row] * kLog2e;
+    // padded query rows get a huge negative score offset: exp2 of it is exactly 0, so they contribute nothing
+    const float a = row < Nq ? -lse[(static_cast<int64_t>(b) * H + h) * Nq + row] * inv_scale : -1e30f;
+    *reinterpret_cast<uint4*>(lse_aug + chunk0) = split3_bf16(a);
+    *reinterpret_cast<uint4*>(d_aug + chunk0) = split3_bf16(-acc);
+  } else if (sub == 1) {
+    *reinterpret_cast<uint4*>(lse_aug + chunk0 + kAugLbo) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(d_aug + chunk0 + kAugLbo) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -220,6 +246,12 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(&sm.dkv_full, 1);
     fence_mbar_init();
   }
+  if (tid < 2 * kAugBytes / 16) {     // constant A tile of the extra k-step: columns 0-2 = 1.0, the rest 0
+    const bool first_half = ((tid >> 3) & 1) == 0;
+    *reinterpret_cast<uint4*>(sm.ones + tid * 16) =
+        first_half ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
   __syncwarp();
   if (warp == 13) {
     tmem_alloc(&sm.tmem_base, 512);
@@ -238,16 +270,17 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mbar_expect_tx(&sm.kv_full, 2 * kTileBytes);
         tma_load_4d(sm.k, &tm_k, &sm.kv_full, 0, head, kv_base, batch);
         tma_load_4d(sm.v, &tm_v, &sm.kv_full, 0, head, kv_base, batch);
-        const float* lse_row = p.lse2 + (static_cast<size_t>(batch) * p.H + head) * p.Nq_pad;
-        const float* ds_row = p.dsum + (static_cast<size_t>(batch) * p.H + head) * p.Nq_pad;
+        const size_t aug_base = (static_cast<size_t>(batch) * p.H + head) * n_steps * (kAugBytes / 2);
+        const __nv_bfloat16* lse_tiles = p.lse_aug + aug_base;
+        const __nv_bfloat16* d_tiles = p.d_aug + aug_base;
         for (int s = 0; s < n_steps; ++s) {
           const int st = s % kQStages;
           const uint32_t ph = (s / kQStages) & 1;
           mbar_wait(&sm.q_empty[st], ph ^ 1);
-          mbar_expect_tx(&sm.q_full[st], kStepBytes + 2 * kStep * 4);
+          mbar_expect_tx(&sm.q_full[st], kStepBytes + 2 * kAugBytes);
           tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, s * kStep, batch);
-          bulk_load_1d(sm.lse2[st], lse_row + s * kStep, kStep * 4, &sm.q_full[st]);
-          bulk_load_1d(sm.dsum[st], ds_row + s * kStep, kStep * 4, &sm.q_full[st]);
+          bulk_load_1d(sm.lse_aug[st], lse_tiles + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
+          bulk_load_1d(sm.d_aug[st], d_tiles + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
           mbar_wait(&sm.do_empty[st], ph ^ 1);
           mbar_expect_tx(&sm.do_full[st], kStepBytes);
           tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, s * kStep, batch);
@@ -264,6 +297,9 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const uint64_t d_q0 = make_smem_desc(smem_u32(sm.q[0]), 16, 1024, kLayoutSW128);      // stages are contiguous
         const uint64_t d_do0 = make_smem_desc(smem_u32(sm.dout[0]), 16, 1024, kLayoutSW128);
         const uint64_t d_ds_mn0 = make_smem_desc(smem_u32(sm.ds[0]), kTileBytes, 1024, kLayoutSW128);
+        const uint64_t d_ones = make_smem_desc(smem_u32(sm.ones), kAugLbo, kAugSbo, 0);
+        const uint64_t d_lse0 = make_smem_desc(smem_u32(sm.lse_aug[0]), kAugLbo, kAugSbo, 0);   // stages contiguous
+        const uint64_t d_d0 = make_smem_desc(smem_u32(sm.d_aug[0]), kAugLbo, kAugSbo, 0);
 
         auto issue_sdp = [&](int s) {            // S^T(s) = K Q_s^T, dP^T(s) = V dO_s^T into buffer s & 1
           const int st = s % kQStages, b = s & 1;
@@ -272,13 +308,15 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tc_fence_after();
           const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
 #pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
+          for (int kk = 0; kk < ((kAblate & 128) ? 0 : kHeadDim / 16); ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
             umma_ts(tmem + kTmemS + b * kStep, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt,
                     kk > 0 ? 1u : 0u);
+          if (!(kAblate & 64)) umma_ss(tmem + kTmemS + b * kStep, d_ones, desc_advance(d_lse0, st * kAugBytes), idesc_nt, 1u);   // - lse/scale
 #pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = V from TMEM
+          for (int kk = 0; kk < ((kAblate & 128) ? 0 : kHeadDim / 16); ++kk)   // A = V from TMEM
             umma_ts(tmem + kTmemDP + b * kStep, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt,
                     kk > 0 ? 1u : 0u);
+          if (!(kAblate & 64)) umma_ss(tmem + kTmemDP + b * kStep, d_ones, desc_advance(d_d0, st * kAugBytes), idesc_nt, 1u);    // - D
           umma_commit(&sm.sdp_full[b]);
         };
 
@@ -297,20 +335,20 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           // dV += P^T(s) dO_s   (A = bf16 P^T, in place in the S buffer: 16 queries = 8 columns per k-step, the
           //                      two 32-query halves start at columns 0 and 32)
 #pragma unroll
-          for (int kk = 0; kk < kStep / 16; ++kk)
+          for (int kk = 0; kk < ((kAblate & 32) ? 0 : kStep / 16); ++kk)
             umma_ts(tmem + kTmemDV, tmem + kTmemS + b * kStep + (kk >> 1) * 32 + (kk & 1) * 8,
                     desc_advance(ddo_s, kk * 2048), idesc_kmn, (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.do_empty[st]);
           // dK += dS^T(s) Q_s   (A = bf16 dS^T, in place in the dP buffer)
 #pragma unroll
-          for (int kk = 0; kk < kStep / 16; ++kk)
+          for (int kk = 0; kk < ((kAblate & 32) ? 0 : kStep / 16); ++kk)
             umma_ts(tmem + kTmemDK, tmem + kTmemDP + b * kStep + (kk >> 1) * 32 + (kk & 1) * 8,
                     desc_advance(dq_s, kk * 2048), idesc_kmn, (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.q_empty[st]);
           LCBI_TR(2, s, 1);
           if (s + 2 < n_steps) issue_sdp(s + 2);
           LCBI_TR(2, s, 2);
-          if (s & 1) {
+          if ((s & 1) && !(kAblate & 2)) {
             // dQ_i = dS(i) K over the whole 128-query tile (A = dS^T read MN-major: both atoms)
             mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
             tc_fence_after();
@@ -332,7 +370,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int row = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t t_dq = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kTmemDQ;
     const bool issuer = (tid == 8 * 32);
-    const int n_tiles = n_steps >> 1;
+    const int n_tiles = (kAblate & 2) ? 0 : (n_steps >> 1);
     for (int i = 0; i < n_tiles; ++i) {
       mbar_wait(&sm.dq_full, i & 1);
       if (issuer) LCBI_TR(3, i, 0);
@@ -344,6 +382,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.dq_empty);
+      if (kAblate & 8) continue;
       if constexpr (kDrainWithRed) {
         // each thread adds its own 256-byte dQ row straight into the fp32 accumulator (16 x red.v4.f32)
         const int q_row = i * kTile + row;
@@ -378,7 +417,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         LCBI_TR(3, i, 1);
       }
     }
-    if (issuer) tma_store_wait_all<0>();
+    if (issuer) tma_store_wait_read<0>();
   } else {
     // ------------------------------------------------------------------ P^T and dS^T in one pass (warps 0-7)
     setmaxnreg_inc<184>();
@@ -405,13 +444,18 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
 
     for (int s = 0; s < n_steps; ++s) {
-      const int st = s % kQStages, b = s & 1, i = s >> 1;
+      const int b = s & 1, i = s >> 1;
       if (lane == 0) LCBI_TR(hh, s, 0);
-      // One wait per step: the issuer waited on q_full/do_full before the GEMMs this commit covers (so lse2 / dsum
-      // of the step are in smem), and the commit also covers dQ(i-2), the last reader of the dS^T smem buffer.
+      // One wait per step: the commit also covers dQ(i-2), the last reader of the dS^T smem buffer.
       mbar_wait(&sm.sdp_full[b], (s >> 1) & 1);
       if (lane == 0) LCBI_TR(hh, s, 1);
       tc_fence_after();
+      if (kAblate & 16) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.pds_full[b]);
+        continue;
+      }
       uint32_t sv[32], dpv[32];
       tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + hh * 32, sv);
       tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
@@ -419,36 +463,16 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (lane == 0) LCBI_TR(hh, s, 2);
       uint32_t pk[16], dsk[16];
       uint8_t* ds_atom = sm.ds[i & 1] + (s & 1) * kTileBytes;
-      // per-query lse2 / dsum: software-pipelined broadcast loads (next group's values in flight while this one computes)
-      float4 l0 = lds128(&sm.lse2[st][hh * 32]), l1 = lds128(&sm.lse2[st][hh * 32 + 4]);
-      float4 d0 = lds128(&sm.dsum[st][hh * 32]), d1 = lds128(&sm.dsum[st][hh * 32 + 4]);
+      // the per-query terms were already added by the tensor core: sv = q.k - lse/scale, dpv = dO.v - D
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {             // 8 query columns -> one 16-byte chunk of dS^T
-        const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        if (g < 3) {
-          l0 = lds128(&sm.lse2[st][hh * 32 + (g + 1) * 8]);
-          l1 = lds128(&sm.lse2[st][hh * 32 + (g + 1) * 8 + 4]);
-          d0 = lds128(&sm.dsum[st][hh * 32 + (g + 1) * 8]);
-          d1 = lds128(&sm.dsum[st][hh * 32 + (g + 1) * 8 + 4]);
-        }
-        float pe[8], de[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pe[e] = fast_exp2(fmaf(__uint_as_float(sv[g * 8 + e]), c, -lv[e]));
-          de[e] = pe[e] * (__uint_as_float(dpv[g * 8 + e]) - dv[e]);
-        }
-        pk[g * 4 + 0] = pack_bf16x2(pe[0], pe[1]);
-        pk[g * 4 + 1] = pack_bf16x2(pe[2], pe[3]);
-        pk[g * 4 + 2] = pack_bf16x2(pe[4], pe[5]);
-        pk[g * 4 + 3] = pack_bf16x2(pe[6], pe[7]);
-        dsk[g * 4 + 0] = pack_bf16x2(de[0], de[1]);
-        dsk[g * 4 + 1] = pack_bf16x2(de[2], de[3]);
-        dsk[g * 4 + 2] = pack_bf16x2(de[4], de[5]);
-        dsk[g * 4 + 3] = pack_bf16x2(de[6], de[7]);
+      for (int e = 0; e < 32; e += 2) {
+        const float p0 = (kAblate & 1) ? __uint_as_float(sv[e]) * c : fast_exp2(__uint_as_float(sv[e]) * c);
+        const float p1 = (kAblate & 1) ? __uint_as_float(sv[e + 1]) * c : fast_exp2(__uint_as_float(sv[e + 1]) * c);
+        pk[e >> 1] = pack_bf16x2(p0, p1);
+        dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
       }
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < ((kAblate & 4) ? 0 : 4); ++g)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
                      "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
       // in place: the packed results overwrite the first 16 of the 32 columns this thread just read
@@ -489,7 +513,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if ((tid & 127) == 0) {
         tma_store_4d(tm, stage, 0, head, kv_base, batch);
         tma_store_commit();
-        tma_store_wait_all<0>();
+        tma_store_wait_read<0>();
       }
     } else {
 #pragma unroll
@@ -506,7 +530,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tma_reduce_add_4d(tm, stage, 0, head, kv_base, batch);
         tma_reduce_add_4d(tm, stage + kTileBytes, 32, head, kv_base, batch);
         tma_store_commit();
-        tma_store_wait_all<0>();
+        tma_store_wait_read<0>();
       }
     }
   }
@@ -548,7 +572,7 @@ extern "C" int lcbi_debug_set_bwd_trace(long long* ptr) {
 size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim) {
   const size_t nq_pad = align_up(static_cast<size_t>(Nq), kTile);
   const size_t acc = align_up(static_cast<size_t>(B) * Nq * H * head_dim * 4, 128);
-  const size_t vec = align_up(static_cast<size_t>(B) * H * nq_pad * 4, 128);
+  const size_t vec = align_up(static_cast<size_t>(B) * H * (nq_pad / kStep) * kAugBytes, 128);
   return acc + 2 * vec;
 }
 
@@ -569,10 +593,11 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
 
   const int nq_pad = static_cast<int>(align_up(static_cast<size_t>(a.Nq), kTile));
   const size_t acc_bytes = align_up(static_cast<size_t>(a.B) * a.Nq * a.H * kHeadDim * 4, 128);
-  const size_t vec_bytes = align_up(static_cast<size_t>(a.B) * a.H * nq_pad * 4, 128);
+  const size_t vec_bytes = align_up(static_cast<size_t>(a.B) * a.H * (nq_pad / kStep) * kAugBytes, 128);
   float* dq_acc = a.accumulate_dq ? reinterpret_cast<float*>(a.dq) : reinterpret_cast<float*>(a.workspace);
-  float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes);
-  float* dsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes + vec_bytes);
+  uint8_t* lse_aug = reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes;
+  uint8_t* d_aug = reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes + vec_bytes;
+  if (!(a.scale > 0.f)) return LCBI_ERR_BAD_ARG;
 
   CUtensorMap tq, tk, tv, tdo, tacc, tdk, tdv;
   if (make_bf16_map(&tq, a.q, a.B, a.H, a.Nq, a.q_strides, kStep) || make_bf16_map(&tk, a.k, a.B, a.H, a.Nk, a.k_strides) ||
@@ -597,8 +622,8 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
     const int threads = 256;
     const int64_t blocks = (rows * 8 + threads - 1) / threads;
     bwd_prep_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(a.o), reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.lse, lse2, dsum,
-        a.B, a.H, a.Nq, nq_pad, a.o_strides[0], a.o_strides[1], a.o_strides[2], a.do_strides[0], a.do_strides[1],
+        reinterpret_cast<const __nv_bfloat16*>(a.o), reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.lse, lse_aug, d_aug,
+        1.0f / a.scale, a.B, a.H, a.Nq, nq_pad, a.o_strides[0], a.o_strides[1], a.o_strides[2], a.do_strides[0], a.do_strides[1],
         a.do_strides[2]);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
@@ -615,8 +640,8 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.Nq_pad = nq_pad;
   p.scale = a.scale;
   p.scale_log2 = a.scale * kLog2e;
-  p.lse2 = lse2;
-  p.dsum = dsum;
+  p.lse_aug = reinterpret_cast<const __nv_bfloat16*>(lse_aug);
+  p.d_aug = reinterpret_cast<const __nv_bfloat16*>(d_aug);
   p.dq_acc = dq_acc;
   p.accumulate_dkv = a.accumulate_dkv;
   dim3 grid((a.Nk + kTile - 1) / kTile, a.H, a.B);

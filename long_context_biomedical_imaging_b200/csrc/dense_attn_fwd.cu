@@ -4,17 +4,20 @@
 // (/root/reference/model/models/backbone_vit.py:191-201): softmax(scale * q k^T) v, without ever
 // materialising the B*H*N*N matrix and reading q/k/v straight out of the (B,N,3,H,d) qkv tensor.
 //
-// One CTA = two 128-row query tiles of one (batch, head) sharing every 64-key K/V tile:
-//   warp 9      TMA producer   (Q0,Q1 once; K_j / V_j through 4-stage rings)
-//   warp 8      UMMA issuer    (S_t = Q_t K_j^T -> TMEM;  O_t += P_t V_j with P_t read from TMEM)
-//   warps 0-3   softmax for query tile 0 (one thread = one query row = one TMEM lane)
-//   warps 4-7   softmax for query tile 1
-// TMEM (512 columns): S_t is DOUBLE-BUFFERED per query tile — S0a [0,64) S0b [64,128) S1a [128,192) S1b [192,256) —
-// so the tensor core computes S_t(j+1) while the softmax group exponentiates S_t(j); O0 [256,320) O1 [320,384);
-// P_t (bf16) overwrites the first 32 columns of the S buffer it came from. The issuer polls the two groups'
-// "P ready" barriers and serves whichever arrives first, so the groups drift out of phase and share the MUFU
-// pipe instead of convoying. Online softmax uses a lazily updated running max (only moved when the new max
-// exceeds it by 2^8) so the O rescale in TMEM is rare.
+// Work item = one 128-row query tile of one (batch, head). The kernel is PERSISTENT: CTA c handles items c, c + grid,
+// c + 2 grid, ... and two CTAs are resident per SM (192 threads, 256 TMEM columns, ~97 KB smem each), so that
+//   * the two tiles on an SM run out of phase and share the MUFU and tensor pipes instead of convoying,
+//   * an item's prologue (Q load, first S) and epilogue (O scale + store) overlap the other CTA's main loop, and the
+//     next item's Q tile and K/V tiles are prefetched while the current item finishes (measured: a non-persistent
+//     one-CTA-per-SM version spent ~5 us of every ~28 us item in launch / prologue / epilogue).
+// Warp roles:
+//   warp 5      TMA producer   (Q per item, double-buffered; K_j / V_j through 4-stage rings that run across items)
+//   warp 4      UMMA issuer    (S = Q K_j^T -> TMEM;  O += P V_j with P read from TMEM)
+//   warps 0-3   softmax + epilogue (one thread = one query row = one TMEM lane)
+// TMEM: S is double-buffered, S_a [0,64) S_b [64,128), so the tensor core computes S(j+1) while the softmax warps
+// exponentiate S(j); O [128,192); P (bf16) overwrites the first 32 columns of the S buffer it came from.
+// Online softmax uses a lazily updated running max (only moved when the new max exceeds it by 2^8) so the O rescale
+// in TMEM is rare. All mbarrier phases are derived from counters that keep running across items.
 #include "lcbi_kernels.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
@@ -29,38 +32,35 @@ constexpr int kHeadDim = 64;
 constexpr int kStages = 4;        // K and V ring depth
 constexpr int kQTileBytes = kBlockM * kHeadDim * 2;   // 16 KB
 constexpr int kKVTileBytes = kBlockN * kHeadDim * 2;  // 8 KB
-constexpr int kNumThreads = 320;
+constexpr int kSoftmaxWarps = 4, kMmaWarp = 4, kTmaWarp = 5;
+constexpr int kNumThreads = 192;
+constexpr int kCtasPerSm = 2;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemO = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-constexpr bool kExpPingPong = false;
-#ifndef LCBI_FWD_STAGGER_NS
-#define LCBI_FWD_STAGGER_NS 0   /* measured: 350 ns stagger gives 0.280 ms vs 0.276 ms in lock-step: no gain */
-#endif
-constexpr unsigned kStaggerNs = LCBI_FWD_STAGGER_NS;
 
-__device__ __forceinline__ constexpr uint32_t tmem_s(int t, int buf) { return t * 128 + buf * 64; }
-__device__ __forceinline__ constexpr uint32_t tmem_o(int t) { return 256 + t * 64; }
+__device__ __forceinline__ constexpr uint32_t tmem_s(int buf) { return buf * 64; }
 
 struct __align__(1024) FwdSmem {
-  uint8_t q[2][kQTileBytes];        // also the O staging tiles for the TMA store
+  uint8_t q[2][kQTileBytes];        // Q of item it in q[it & 1]; reused as the O staging tile of that item
   uint8_t k[kStages][kKVTileBytes];
   uint8_t v[kStages][kKVTileBytes];
-  uint64_t q_full[2];
+  uint64_t q_full[2], q_free[2];
   uint64_t k_full[kStages], k_empty[kStages];
   uint64_t v_full[kStages], v_empty[kStages];
-  uint64_t s_full[2][2], p_full[2][2], pv_done[2], o_full[2];
+  uint64_t s_full[2], p_full[2], pv_done, o_full;
   uint32_t tmem_base;
 };
 
 #ifdef LCBI_TRACE
-// debug build only (tools/trace_dense.py): per-role clock64 timestamps of CTA (0,0,0)
+// debug build only (tools/trace_dense.py): per-role clock64 timestamps of the first item of CTA 0
 __device__ long long* g_fwd_trace = nullptr;
-#define LCBI_TR_INIT() \
-  long long* const lcbi_tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_fwd_trace : nullptr
-#define LCBI_TR(role, step, ev)                                                            \
-  do {                                                                                     \
-    if (lcbi_tr != nullptr && (step) < 32) lcbi_tr[((role) * 32 + (step)) * 8 + (ev)] = clock64(); \
+#define LCBI_TR_INIT() long long* const lcbi_tr = (blockIdx.x == 0) ? g_fwd_trace : nullptr
+#define LCBI_TR(role, step, ev)                                                                       \
+  do {                                                                                                \
+    if (lcbi_tr != nullptr && it == 0 && (step) < 32) lcbi_tr[((role) * 32 + (step)) * 8 + (ev)] = clock64(); \
   } while (0)
 #else
 #define LCBI_TR_INIT() do { } while (0)
@@ -69,11 +69,19 @@ __device__ long long* g_fwd_trace = nullptr;
 
 struct FwdParams {
   int B, H, Nq, Nk;
+  int n_q_tiles, n_items;
   float scale_log2;   // scale * log2(e)
   float* lse;         // (B, H, Nq) natural log
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+// Timing-only ablations (results become wrong; every barrier still fires): bit 0 no exp2, bit 1 no row-max pass,
+// bit 2 softmax warps only wait and arrive.
+#ifndef LCBI_FWD_ABLATE
+#define LCBI_FWD_ABLATE 0
+#endif
+constexpr int kAblate = LCBI_FWD_ABLATE;
+
+__global__ void __launch_bounds__(kNumThreads, kCtasPerSm)
 dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                       const FwdParams p) {
@@ -83,34 +91,18 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  // 1-D grid, heavy CTAs first: every (batch, head) has n_full query-tile pairs with two full tiles and possibly one
-  // lighter trailing pair; scheduling the light ones last shortens the final partial wave.
-  const int n_full = p.Nq / (2 * kBlockM);
-  const int bh_total = p.B * p.H;
-  int pair, bh;
-  if (static_cast<int>(blockIdx.x) < n_full * bh_total) {
-    pair = blockIdx.x % n_full;
-    bh = blockIdx.x / n_full;
-  } else {
-    pair = n_full;
-    bh = blockIdx.x - n_full * bh_total;
-  }
-  const int head = bh % p.H, batch = bh / p.H;
-  const int q_base = pair * (2 * kBlockM);
-  const bool tile1_active = (q_base + kBlockM) < p.Nq;
   const int n_kv = (p.Nk + kBlockN - 1) / kBlockN;
   LCBI_TR_INIT();
 
   if (tid == 0) {
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&sm.q_full[t], 1);
-      mbar_init(&sm.pv_done[t], 1);
-      mbar_init(&sm.o_full[t], 1);
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&sm.s_full[t][b], 1);
-        mbar_init(&sm.p_full[t][b], 4);    // one arrive per softmax warp
-      }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.q_full[b], 1);
+      mbar_init(&sm.q_free[b], 1);
+      mbar_init(&sm.s_full[b], 1);
+      mbar_init(&sm.p_full[b], kSoftmaxWarps);    // one arrive per softmax warp
     }
+    mbar_init(&sm.pv_done, 1);
+    mbar_init(&sm.o_full, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.k_full[s], 1);
       mbar_init(&sm.k_empty[s], 1);
@@ -120,11 +112,11 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 8) {
-    tmem_alloc(&sm.tmem_base, 512);
+  if (warp == kMmaWarp) {
+    tmem_alloc(&sm.tmem_base, kTmemCols);
     tmem_relinquish();
   }
-  if (warp == 9 && elect_one()) {
+  if (warp == kTmaWarp && elect_one()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -135,124 +127,130 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 9) {
+  // item -> (batch, head, first query row): adjacent items are adjacent query tiles of one (batch, head), so the CTAs
+  // running at any moment read a small set of K/V tensors (L2-resident)
+  auto decode = [&](int item, int& batch, int& head, int& q_base) {
+    const int tile = item % p.n_q_tiles, bh = item / p.n_q_tiles;
+    head = bh % p.H;
+    batch = bh / p.H;
+    q_base = tile * kBlockM;
+  };
+
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      mbar_expect_tx(&sm.q_full[0], kQTileBytes);
-      tma_load_4d(sm.q[0], &tm_q, &sm.q_full[0], 0, head, q_base, batch);
-      if (tile1_active) {
-        mbar_expect_tx(&sm.q_full[1], kQTileBytes);
-        tma_load_4d(sm.q[1], &tm_q, &sm.q_full[1], 0, head, q_base + kBlockM, batch);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        mbar_wait(&sm.k_empty[s], ph ^ 1);
-        mbar_expect_tx(&sm.k_full[s], kKVTileBytes);
-        tma_load_4d(sm.k[s], &tm_k, &sm.k_full[s], 0, head, j * kBlockN, batch);
-        mbar_wait(&sm.v_empty[s], ph ^ 1);
-        mbar_expect_tx(&sm.v_full[s], kKVTileBytes);
-        tma_load_4d(sm.v[s], &tm_v, &sm.v_full[s], 0, head, j * kBlockN, batch);
+      int g = 0;   // K/V tiles issued so far (ring position), runs across items
+      int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        int batch, head, q_base;
+        decode(item, batch, head, q_base);
+        const int qb = it & 1;
+        if (it >= 2) mbar_wait(&sm.q_free[qb], ((it >> 1) - 1) & 1);   // O store of item it-2 has left the buffer
+        mbar_expect_tx(&sm.q_full[qb], kQTileBytes);
+        tma_load_4d(sm.q[qb], &tm_q, &sm.q_full[qb], 0, head, q_base, batch);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const int s = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
+          mbar_wait(&sm.k_empty[s], ph ^ 1);
+          mbar_expect_tx(&sm.k_full[s], kKVTileBytes);
+          tma_load_4d(sm.k[s], &tm_k, &sm.k_full[s], 0, head, j * kBlockN, batch);
+          mbar_wait(&sm.v_empty[s], ph ^ 1);
+          mbar_expect_tx(&sm.v_full[s], kKVTileBytes);
+          tma_load_4d(sm.v[s], &tm_v, &sm.v_full[s], 0, head, j * kBlockN, batch);
+        }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ UMMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);  // P V   : V is MN-major
-      const uint32_t q_addr[2] = {smem_u32(sm.q[0]), smem_u32(sm.q[1])};
-      const int n_tiles = tile1_active ? 2 : 1;
-
-      auto issue_s = [&](int t, int j) {        // S_t(j) -> buffer j & 1
-        const uint32_t k_addr = smem_u32(sm.k[j % kStages]);
+      int g0 = 0;  // global index of this item's first K/V tile
+      int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
+        const uint32_t q_addr = smem_u32(sm.q[it & 1]);
+        auto issue_s = [&](int g) {               // S(g) -> buffer g & 1
+          const uint32_t k_addr = smem_u32(sm.k[g % kStages]);
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-          const uint64_t da = make_smem_desc(q_addr[t] + kk * 32, 16, 1024, kLayoutSW128);
-          const uint64_t db = make_smem_desc(k_addr + kk * 32, 16, 1024, kLayoutSW128);
-          umma_ss(tmem + tmem_s(t, j & 1), da, db, idesc_s, kk > 0 ? 1u : 0u);
-        }
-        umma_commit(&sm.s_full[t][j & 1]);
-      };
-      auto issue_pv = [&](int t, int j) {       // O_t += P_t(j) V_j
-        const uint32_t v_addr = smem_u32(sm.v[j % kStages]);
-#pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk) {
-          const uint64_t db = make_smem_desc(v_addr + kk * 2048, 16, 1024, kLayoutSW128);
-          umma_ts(tmem + tmem_o(t), tmem + tmem_s(t, j & 1) + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(&sm.pv_done[t]);
-      };
-
-      mbar_wait(&sm.q_full[0], 0);
-      if (tile1_active) mbar_wait(&sm.q_full[1], 0);
-      for (int j0 = 0; j0 < 2 && j0 < n_kv; ++j0) {
-        mbar_wait(&sm.k_full[j0 % kStages], 0);
-        tc_fence_after();
-        for (int t = 0; t < n_tiles; ++t) issue_s(t, j0);
-        umma_commit(&sm.k_empty[j0 % kStages]);
-      }
-
-      for (int j = 0; j < n_kv; ++j) {
-        const bool has_next = (j + 2) < n_kv;
-        mbar_wait(&sm.v_full[j % kStages], (j / kStages) & 1);
-        if (has_next) mbar_wait(&sm.k_full[(j + 2) % kStages], ((j + 2) / kStages) & 1);
-        uint32_t pending = (1u << n_tiles) - 1u;
-        const long long t_start = clock64();
-        while (pending) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if ((pending >> t) & 1u) {
-              if (mbar_try_wait(&sm.p_full[t][j & 1], (j >> 1) & 1)) {
-                LCBI_TR(2, j, t * 3);
-                tc_fence_after();
-                issue_pv(t, j);
-                if (has_next) issue_s(t, j + 2);
-                else if (j == n_kv - 1) umma_commit(&sm.o_full[t]);
-                LCBI_TR(2, j, t * 3 + 1);
-                pending &= ~(1u << t);
-              }
-            }
+          for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+            const uint64_t da = make_smem_desc(q_addr + kk * 32, 16, 1024, kLayoutSW128);
+            const uint64_t db = make_smem_desc(k_addr + kk * 32, 16, 1024, kLayoutSW128);
+            umma_ss(tmem + tmem_s(g & 1), da, db, idesc_s, kk > 0 ? 1u : 0u);
           }
-          if (clock64() - t_start > LCBI_WATCHDOG_CYCLES) {
-            printf("lcbi watchdog: fwd issuer stuck (block %d,%d,%d step %d pending %u)\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, j, pending);
-            __trap();
+          umma_commit(&sm.s_full[g & 1]);
+        };
+        auto issue_pv = [&](int g, bool first) {  // O (+)= P(g) V(g)
+          const uint32_t v_addr = smem_u32(sm.v[g % kStages]);
+#pragma unroll
+          for (int kk = 0; kk < kBlockN / 16; ++kk) {
+            const uint64_t db = make_smem_desc(v_addr + kk * 2048, 16, 1024, kLayoutSW128);
+            umma_ts(tmem + kTmemO, tmem + tmem_s(g & 1) + kk * 8, db, idesc_o, (!first || kk > 0) ? 1u : 0u);
           }
+          umma_commit(&sm.pv_done);
+        };
+
+        mbar_wait(&sm.q_full[it & 1], (it >> 1) & 1);
+        for (int j0 = 0; j0 < 2 && j0 < n_kv; ++j0) {
+          const int g = g0 + j0;
+          mbar_wait(&sm.k_full[g % kStages], (g / kStages) & 1);
+          tc_fence_after();
+          issue_s(g);
+          umma_commit(&sm.k_empty[g % kStages]);
         }
-        umma_commit(&sm.v_empty[j % kStages]);
-        if (has_next) umma_commit(&sm.k_empty[(j + 2) % kStages]);
+        for (int j = 0; j < n_kv; ++j) {
+          const int g = g0 + j;
+          const bool has_next = (j + 2) < n_kv;
+          // the waits that do not depend on the softmax warps come first, so their latency hides behind that work
+          mbar_wait(&sm.v_full[g % kStages], (g / kStages) & 1);
+          if (has_next) mbar_wait(&sm.k_full[(g + 2) % kStages], ((g + 2) / kStages) & 1);
+          mbar_wait(&sm.p_full[g & 1], (g >> 1) & 1);
+          LCBI_TR(1, j, 0);
+          tc_fence_after();
+          issue_pv(g, j == 0);
+          if (has_next) issue_s(g + 2);
+          else if (j == n_kv - 1) umma_commit(&sm.o_full);
+          umma_commit(&sm.v_empty[g % kStages]);
+          if (has_next) umma_commit(&sm.k_empty[(g + 2) % kStages]);
+          LCBI_TR(1, j, 1);
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue
-    const int t = warp >> 2;                   // query tile handled by this warpgroup
-    const int row = tid & 127;                 // row inside the tile == TMEM lane
-    if (t == 0 || tile1_active) {
-      const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t t_o = tmem + lane_sel + tmem_o(t);
-      const float c = p.scale_log2;
+    const int row = tid;                       // row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t t_o = tmem + lane_sel + kTmemO;
+    const float c = p.scale_log2;
+    int g0 = 0;
+    int it = 0;
+    int store_pending = -1;                    // Q/O buffer whose TMA store has not been waited for yet (thread 0)
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
+      int batch, head, q_base;
+      decode(item, batch, head, q_base);
       float m_used = -INFINITY;  // running max actually subtracted (raw score units)
       float l = 0.f;
-      // Optional strict alternation of the two groups' exp phases (named barriers 3 / 4 hand a token back and
-      // forth). Measured on B200 (profiles/r01_fwd_trace_pingpong.log): one warp per scheduler cannot saturate the
-      // MUFU pipe (725 cycles per 64 exps instead of 512), so letting both groups exponentiate concurrently is
-      // faster (0.276 ms vs 0.300 ms at cfg3 B=16). Kept for experiments, off by default.
-      const bool pingpong = kExpPingPong && tile1_active;
-      if (pingpong && t == 1) named_bar_arrive(3, 256);
 
       for (int j = 0; j < n_kv; ++j) {
-        const int buf = j & 1;
-        const uint32_t t_s = tmem + lane_sel + tmem_s(t, buf);
-        if (row == 0) LCBI_TR(t, j, 0);
-        mbar_wait(&sm.s_full[t][buf], (j >> 1) & 1);
-        if (kStaggerNs > 0 && t == 1 && j == 0) __nanosleep(kStaggerNs);   // one-off phase offset between the groups
-        if (row == 0) LCBI_TR(t, j, 1);
+        const int g = g0 + j;
+        const int buf = g & 1;
+        const uint32_t t_s = tmem + lane_sel + tmem_s(buf);
+        if (row == 0) LCBI_TR(0, j, 0);
+        mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
+        if (row == 0) LCBI_TR(0, j, 1);
         tc_fence_after();
+        if (kAblate & 4) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.p_full[buf]);
+          l = 1.f;
+          m_used = 0.f;
+          continue;
+        }
         uint32_t sr[64];
         tmem_ld_x32(t_s, sr);
         tmem_ld_x32(t_s + 32, sr + 32);
         tmem_ld_wait();
-        if (row == 0) LCBI_TR(t, j, 2);
+        if (row == 0) LCBI_TR(0, j, 2);
 
         const int valid = p.Nk - j * kBlockN;  // >= 1
         if (valid < kBlockN) {
@@ -263,7 +261,7 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]), mx2 = __uint_as_float(sr[2]),
               mx3 = __uint_as_float(sr[3]);
 #pragma unroll
-        for (int i = 4; i < kBlockN; i += 4) {
+        for (int i = 4; i < ((kAblate & 2) ? 4 : kBlockN); i += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
           mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
@@ -277,9 +275,9 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           if (need) m_used = m_new;
           l *= alpha;
           if (j > 0) {
-            // O_t must be quiescent: P_t(j-1) V has completed (the S buffers are double-buffered, so s_full
-            // alone does not imply it) and P_t(j) V is not issued before this group signals p_full.
-            mbar_wait(&sm.pv_done[t], (j - 1) & 1);
+            // O must be quiescent: P(g-1) V has completed (the S buffers are double-buffered, so s_full alone
+            // does not imply it) and P(g) V is not issued before this warp group signals p_full.
+            mbar_wait(&sm.pv_done, (g - 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -293,43 +291,55 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
         }
 
-        if (pingpong) named_bar_sync(3 + t, 256);
-        if (row == 0) LCBI_TR(t, j, 3);
+        if (row == 0) LCBI_TR(0, j, 3);
         const float mc = m_used * c;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < kBlockN; i += 4) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(sr[i]), c, -mc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), c, -mc));
-          const float e2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
-          const float e3 = fast_exp2(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
+          auto ex = [](float x) { return (kAblate & 1) ? x : fast_exp2(x); };
+          const float e0 = ex(fmaf(__uint_as_float(sr[i]), c, -mc));
+          const float e1 = ex(fmaf(__uint_as_float(sr[i + 1]), c, -mc));
+          const float e2 = ex(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
+          const float e3 = ex(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
           s0 += e0; s1 += e1; s2 += e2; s3 += e3;
           pk[i / 2] = pack_bf16x2(e0, e1);
           pk[i / 2 + 1] = pack_bf16x2(e2, e3);
         }
         l += (s0 + s1) + (s2 + s3);
-        if (pingpong) named_bar_arrive(4 - t, 256);
-        if (row == 0) LCBI_TR(t, j, 4);
+        if (row == 0) LCBI_TR(0, j, 4);
         tmem_st_x32(t_s, pk);
         tmem_st_wait();
-        if (row == 0) LCBI_TR(t, j, 5);
+        if (row == 0) LCBI_TR(0, j, 5);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.p_full[t][buf]);
-        if (row == 0) LCBI_TR(t, j, 6);
+        if (lane == 0) mbar_arrive(&sm.p_full[buf]);
+        if (row == 0) LCBI_TR(0, j, 6);
+
+        if (j == 1 && tid == 0 && store_pending >= 0) {
+          // the previous item's O store has certainly been read out of its staging tile by now: hand the buffer back
+          // to the producer (it becomes the Q tile of the item after this one)
+          tma_store_wait_read<0>();
+          mbar_arrive(&sm.q_free[store_pending]);
+          store_pending = -1;
+        }
       }
 
-      if (pingpong && t == 0) named_bar_sync(3, 256);   // absorb the partner's last token
-      // ---- epilogue: O / l -> bf16 -> swizzled smem tile (reuses the Q tile) -> TMA store
-      mbar_wait(&sm.o_full[t], 0);
+      // ---- epilogue: O / l -> bf16 -> swizzled smem tile (the item's Q tile, dead by now) -> TMA store
+      mbar_wait(&sm.o_full, it & 1);
       tc_fence_after();
       uint32_t o[64];
       tmem_ld_x32(t_o, o);
       tmem_ld_x32(t_o + 32, o + 32);
       tmem_ld_wait();
+      tc_fence_before();
+      if (tid == 0 && store_pending >= 0) {     // only when an item has fewer than two K/V tiles
+        tma_store_wait_read<0>();
+        mbar_arrive(&sm.q_free[store_pending]);
+        store_pending = -1;
+      }
       const float inv_l = 1.0f / l;
-      uint8_t* stage = sm.q[t];
+      uint8_t* stage = sm.q[it & 1];
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16) {
         uint4 val;
@@ -339,22 +349,23 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         val.w = pack_bf16x2(__uint_as_float(o[c16 * 8 + 6]) * inv_l, __uint_as_float(o[c16 * 8 + 7]) * inv_l);
         *reinterpret_cast<uint4*>(stage + sw128_offset(row, c16)) = val;
       }
-      const int q_row = q_base + t * kBlockM + row;
+      const int q_row = q_base + row;
       if (q_row < p.Nq)
         p.lse[(static_cast<size_t>(batch) * p.H + head) * p.Nq + q_row] = (m_used * c + log2f(l)) * kLn2;
       fence_proxy_async_smem();
-      named_bar_sync(1 + t, 128);
-      if ((tid & 127) == 0) {
-        tma_store_4d(&tm_o, stage, 0, head, q_base + t * kBlockM, batch);
+      named_bar_sync(1, kSoftmaxWarps * 32);
+      if (tid == 0) {
+        tma_store_4d(&tm_o, stage, 0, head, q_base, batch);
         tma_store_commit();
-        tma_store_wait_all<0>();
+        store_pending = it & 1;
       }
     }
+    if (tid == 0 && store_pending >= 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace
@@ -396,11 +407,20 @@ int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
   FwdParams p;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
+  p.n_q_tiles = (a.Nq + kBlockM - 1) / kBlockM;
+  p.n_items = p.n_q_tiles * a.H * a.B;
   p.scale_log2 = a.scale * kLog2e;
   p.lse = a.lse;
-  dim3 grid(((a.Nq + 2 * kBlockM - 1) / (2 * kBlockM)) * a.H * a.B);
+  dim3 grid(p.n_items < kCtasPerSm * num_sms ? p.n_items : kCtasPerSm * num_sms);
   dense_attn_fwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, to, p);
   return set_cuda_error(cudaGetLastError());
 }

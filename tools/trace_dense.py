@@ -58,8 +58,8 @@ if __name__ == "__main__":
         sys.exit(0)
     t = trace.cpu().view(3, 32, 8)
     t0 = int(t[t > 0].min())
-    names = {0: "WG0", 1: "WG1", 2: "MMA"}
-    for role in range(3):
+    names = {0: "SOFTMAX", 1: "MMA", 2: "-"}
+    for role in range(2):
         print(names[role])
         for step in range(int(os.environ.get('TR_STEPS', 27))):
             row = [int(x) - t0 if x > 0 else -1 for x in t[role, step]]
