@@ -84,6 +84,17 @@ struct __align__(1024) BwdSmem {
 
 #ifdef LCBI_TRACE
 __device__ long long* g_bwd_trace = nullptr;
+__device__ long long* g_bwd_cta_times = nullptr;   // per CTA: smid, globaltimer at start / first step / last step / exit
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define LCBI_CTA_T(slot)                                                                                   \
+  do {                                                                                                     \
+    if (g_bwd_cta_times != nullptr)                                                                        \
+      g_bwd_cta_times[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = global_ns(); \
+  } while (0)
 #define LCBI_TR_INIT() \
   long long* const lcbi_tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_bwd_trace : nullptr
 #define LCBI_TR(role, step, ev)                                                            \
@@ -93,6 +104,7 @@ __device__ long long* g_bwd_trace = nullptr;
 #else
 #define LCBI_TR_INIT() do { } while (0)
 #define LCBI_TR(role, step, ev) do { } while (0)
+#define LCBI_CTA_T(slot) do { } while (0)
 #endif
 
 struct BwdParams {
@@ -227,8 +239,31 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int kv_base = kv_tile * kTile;
   const int n_steps = p.Nq_pad / kStep;      // 64-query steps; even because Nq_pad is a multiple of 128
   LCBI_TR_INIT();
-
+#ifdef LCBI_TRACE
   if (tid == 0) {
+    LCBI_CTA_T(0);
+    if (g_bwd_cta_times != nullptr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      g_bwd_cta_times[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 7] = smid;
+    }
+  }
+#endif
+
+  // The TMA warp initialises the barriers and starts the K/V and first Q/dO loads right away, before the CTA-wide
+  // sync below (TMEM allocation, constant tile): measured, K/V reach TMEM ~0.3 us earlier per CTA.
+  const size_t aug_base = (static_cast<size_t>(batch) * p.H + head) * n_steps * (kAugBytes / 2);
+  const int n_prefill = n_steps < kQStages ? n_steps : kQStages;
+  auto load_step = [&](int s) {                // Q_s with its row terms, and dO_s, into ring stage s % kQStages
+    const int st = s % kQStages;
+    mbar_expect_tx(&sm.q_full[st], kStepBytes + 2 * kAugBytes);
+    tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, s * kStep, batch);
+    bulk_load_1d(sm.lse_aug[st], p.lse_aug + aug_base + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
+    bulk_load_1d(sm.d_aug[st], p.d_aug + aug_base + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
+    mbar_expect_tx(&sm.do_full[st], kStepBytes);
+    tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, s * kStep, batch);
+  };
+  if (warp == 12 && elect_one()) {
     mbar_init(&sm.kv_full, 1);
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(&sm.q_full[s], 1);
@@ -245,6 +280,10 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(&sm.dq_empty, 4);        // one arrive per drain warp
     mbar_init(&sm.dkv_full, 1);
     fence_mbar_init();
+    mbar_expect_tx(&sm.kv_full, 2 * kTileBytes);
+    tma_load_4d(sm.k, &tm_k, &sm.kv_full, 0, head, kv_base, batch);
+    tma_load_4d(sm.v, &tm_v, &sm.kv_full, 0, head, kv_base, batch);
+    for (int s = 0; s < n_prefill; ++s) load_step(s);
   }
   if (tid < 2 * kAugBytes / 16) {     // constant A tile of the extra k-step: columns 0-2 = 1.0, the rest 0
     const bool first_half = ((tid >> 3) & 1) == 0;
@@ -267,23 +306,12 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (warp == 12) {
       // ---------------------------------------------------------------- TMA producer
       if (elect_one()) {
-        mbar_expect_tx(&sm.kv_full, 2 * kTileBytes);
-        tma_load_4d(sm.k, &tm_k, &sm.kv_full, 0, head, kv_base, batch);
-        tma_load_4d(sm.v, &tm_v, &sm.kv_full, 0, head, kv_base, batch);
-        const size_t aug_base = (static_cast<size_t>(batch) * p.H + head) * n_steps * (kAugBytes / 2);
-        const __nv_bfloat16* lse_tiles = p.lse_aug + aug_base;
-        const __nv_bfloat16* d_tiles = p.d_aug + aug_base;
-        for (int s = 0; s < n_steps; ++s) {
+        for (int s = n_prefill; s < n_steps; ++s) {
           const int st = s % kQStages;
           const uint32_t ph = (s / kQStages) & 1;
           mbar_wait(&sm.q_empty[st], ph ^ 1);
-          mbar_expect_tx(&sm.q_full[st], kStepBytes + 2 * kAugBytes);
-          tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, s * kStep, batch);
-          bulk_load_1d(sm.lse_aug[st], lse_tiles + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
-          bulk_load_1d(sm.d_aug[st], d_tiles + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
           mbar_wait(&sm.do_empty[st], ph ^ 1);
-          mbar_expect_tx(&sm.do_full[st], kStepBytes);
-          tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, s * kStep, batch);
+          load_step(s);
         }
       }
     } else if (warp == 13) {
@@ -301,11 +329,12 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const uint64_t d_lse0 = make_smem_desc(smem_u32(sm.lse_aug[0]), kAugLbo, kAugSbo, 0);   // stages contiguous
         const uint64_t d_d0 = make_smem_desc(smem_u32(sm.d_aug[0]), kAugLbo, kAugSbo, 0);
 
+        auto wait_sdp_operands = [&](int s) {   // Q_s (+ row terms) and dO_s have landed
+          mbar_wait(&sm.q_full[s % kQStages], (s / kQStages) & 1);
+          mbar_wait(&sm.do_full[s % kQStages], (s / kQStages) & 1);
+        };
         auto issue_sdp = [&](int s) {            // S^T(s) = K Q_s^T, dP^T(s) = V dO_s^T into buffer s & 1
           const int st = s % kQStages, b = s & 1;
-          mbar_wait(&sm.q_full[st], (s / kQStages) & 1);
-          mbar_wait(&sm.do_full[st], (s / kQStages) & 1);
-          tc_fence_after();
           const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
 #pragma unroll
           for (int kk = 0; kk < ((kAblate & 128) ? 0 : kHeadDim / 16); ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
@@ -322,12 +351,21 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
         mbar_wait(&sm.kv_full, 0);
         mbar_wait(&sm.kvt_full, 0);      // K, V copied into TMEM by the compute warps
+        wait_sdp_operands(0);
         tc_fence_after();
         issue_sdp(0);
-        if (n_steps > 1) issue_sdp(1);
+        if (n_steps > 1) {
+          wait_sdp_operands(1);
+          tc_fence_after();
+          issue_sdp(1);
+        }
 
         for (int s = 0; s < n_steps; ++s) {
           const int st = s % kQStages, b = s & 1, i = s >> 1;
+          // every wait that does not depend on the compute warps comes first, so its latency hides behind their work
+          // and the GEMMs below go out back to back once P^T / dS^T of the step are ready
+          if (s + 2 < n_steps) wait_sdp_operands(s + 2);
+          if ((s & 1) && !(kAblate & 2)) mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
           mbar_wait(&sm.pds_full[b], (s >> 1) & 1);
           LCBI_TR(2, s, 0);
           tc_fence_after();
@@ -350,8 +388,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           LCBI_TR(2, s, 2);
           if ((s & 1) && !(kAblate & 2)) {
             // dQ_i = dS(i) K over the whole 128-query tile (A = dS^T read MN-major: both atoms)
-            mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
-            tc_fence_after();
             const uint64_t dds_mn = desc_advance(d_ds_mn0, (i & 1) * 2 * kTileBytes);
 #pragma unroll
             for (int kk = 0; kk < kTile / 16; ++kk)
@@ -443,8 +479,10 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (lane == 0) mbar_arrive(&sm.kvt_full);
     }
 
+    if (tid == 0) LCBI_CTA_T(1);               // K/V are in TMEM
     for (int s = 0; s < n_steps; ++s) {
       const int b = s & 1, i = s >> 1;
+      if (tid == 0 && s == 1) LCBI_CTA_T(2);   // first step done
       if (lane == 0) LCBI_TR(hh, s, 0);
       // One wait per step: the commit also covers dQ(i-2), the last reader of the dS^T smem buffer.
       mbar_wait(&sm.sdp_full[b], (s >> 1) & 1);
@@ -488,7 +526,9 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
 
     // ---- epilogue: warps 0-3 drain dV, warps 4-7 drain dK (scaled)
+    if (tid == 0) LCBI_CTA_T(3);               // last step handed to the tensor core
     mbar_wait(&sm.dkv_full, 0);
+    if (tid == 0) LCBI_CTA_T(4);               // every GEMM retired
     tc_fence_after();
     uint32_t r[64];
     const uint32_t t_src = tmem + lane_sel + (hh ? kTmemDK : kTmemDV);
@@ -499,6 +539,8 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     uint8_t* stage = hh ? sm.q[0] : sm.dout[0];   // 32 KB each (all stages), free once every MMA retired
     const CUtensorMap* tm = hh ? &tm_dk : &tm_dv;
     if (!p.accumulate_dkv) {
+      // (writing the rows straight from registers with 16-byte st.global was measured: 3.0 us per CTA instead of
+      // 1.6 us for this staged TMA store, the row stride of the qkv layout makes every store a partial sector)
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16) {
         uint4 val;
@@ -537,7 +579,9 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) LCBI_CTA_T(5);
   if (warp == 13) tmem_dealloc(tmem, 512);
+  if (tid == 0) LCBI_CTA_T(6);
 }
 
 int make_bf16_map(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t* st, int box_rows = kTile) {
@@ -566,6 +610,9 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #ifdef LCBI_TRACE
 extern "C" int lcbi_debug_set_bwd_trace(long long* ptr) {
   return static_cast<int>(cudaMemcpyToSymbol(g_bwd_trace, &ptr, sizeof(ptr)));
+}
+extern "C" int lcbi_debug_set_bwd_cta_times(long long* ptr) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_bwd_cta_times, &ptr, sizeof(ptr)));
 }
 #endif
 
