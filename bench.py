@@ -222,6 +222,10 @@ def run_cfg5(args, dist, rank, world, local_rank):
     dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of dense_attn_bwd_kernel at 16 volumes (276.9 MB + 127.1 MB), per volume
+BWD_DRAM_BYTES_PER_VOLUME = (276_902_400 + 127_062_784) // 16
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -385,7 +389,9 @@ def main():
             "tensor_frac_of_measured_peak": step_tflops / peaks["bf16_tflops"],
             "roofline": {"bound": "tensor", "kernel": "dense_attn_bwd launch group (prep + bwd_main + finish)",
                          "achieved": bwd_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": bwd_tflops / peaks["bf16_tflops"], "traffic": None,
+                         "frac": bwd_tflops / peaks["bf16_tflops"], "traffic": BWD_DRAM_BYTES_PER_VOLUME * B,
+                         "traffic_unit": "bytes per launch (dram read + write of dense_attn_bwd_kernel, one ncu --set full "
+                                         "capture at 16 volumes: profiles/r01_ncu_dense_v4_summary.csv, scaled by volumes)",
                          "peak_source": peaks["source"] + " (burst)", "peak_sustained": peaks["bf16_tflops_sustained"],
                          "algorithmic_flops_per_launch": bwd_flops, "avg_launch_ms": bwd_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,

@@ -57,46 +57,39 @@ __host__ __device__ constexpr int aug_chunk_offset(int row, int khalf) {   // by
 // place, the first half of the columns their owner thread read (thread (row, hh) owns columns [32hh, 32hh+32) of a
 // buffer and writes 16 packed columns at [32hh, 32hh+16)); K and V sit in TMEM as the A operands of S^T / dP^T.
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemK = 448, kTmemV = 480;
-constexpr bool kDrainWithRed = false;
-// Timing-only ablations (results become wrong; every barrier still fires): bit 0 no exp2, bit 1 no dQ GEMM/drain,
-// bit 2 no dS^T smem store, bit 3 drain without staging/TMA reduce, bit 4 compute warps only wait and arrive,
-// bit 5 no dV/dK GEMMs, bit 6 no extra (row-term) k-steps, bit 7 no S^T/dP^T GEMMs.
-#ifndef LCBI_BWD_ABLATE
-#define LCBI_BWD_ABLATE 0
-#endif
-constexpr int kAblate = LCBI_BWD_ABLATE;   // dQ partials: red.global.add.v4.f32 from registers (no smem staging)
+   // dQ partials: red.global.add.v4.f32 from registers (no smem staging)
 
 struct __align__(1024) BwdSmem {
-  uint8_t k[kTileBytes];
-  uint8_t v[kTileBytes];
+  uint8_t k[2][kTileBytes];             // K of item it in k[it & 1]: the next item's K is prefetched during this one
+  uint8_t v[kTileBytes];                // only read by the copy into TMEM, so the next item's V can follow early too
   uint8_t q[kQStages][kStepBytes];      // 64-query tiles; together also the dK staging area of the epilogue
   uint8_t dout[kQStages][kStepBytes];   // likewise dV staging
   uint8_t ds[2][2 * kTileBytes];        // dS^T per 128-query tile (double-buffered): two [128 keys x 64 queries] atoms
-  uint8_t dq_stage[2 * kTileBytes];     // two [128 queries x 32 fp32] SW128 tiles
+  uint8_t dq_stage[kTileBytes];         // one [128 queries x 32 fp32] SW128 tile (a dQ tile goes out in two halves)
   uint8_t lse_aug[kQStages][kAugBytes];   // per-query -lse/scale as the B operand of one extra k-step of S^T
   uint8_t d_aug[kQStages][kAugBytes];     // per-query -D likewise for dP^T
   uint8_t ones[2 * kAugBytes];            // [128 keys x 16] constant A operand of those k-steps: (1, 1, 1, 0, ...)
-  uint64_t kv_full;
+  uint64_t k_full[2], v_full;
   uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
-  uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full;
+  uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full, dkv_drained;
   uint32_t tmem_base;
 };
 
 #ifdef LCBI_TRACE
 __device__ long long* g_bwd_trace = nullptr;
-__device__ long long* g_bwd_cta_times = nullptr;   // per CTA: smid, globaltimer at start / first step / last step / exit
+__device__ long long* g_bwd_item_times = nullptr;   // [cta][item (<= 32)][8] globaltimer stamps of compute thread 0
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define LCBI_CTA_T(slot)                                                                                   \
-  do {                                                                                                     \
-    if (g_bwd_cta_times != nullptr)                                                                        \
-      g_bwd_cta_times[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = global_ns(); \
+#define LCBI_ITEM_T(slot)                                                                              \
+  do {                                                                                                 \
+    if (g_bwd_item_times != nullptr && tid == 0 && it < 32)                                            \
+      g_bwd_item_times[(static_cast<size_t>(blockIdx.x) * 32 + it) * 8 + (slot)] = global_ns();       \
   } while (0)
 #define LCBI_TR_INIT() \
-  long long* const lcbi_tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_bwd_trace : nullptr
+  long long* const lcbi_tr = (blockIdx.x == 0) ? g_bwd_trace : nullptr
 #define LCBI_TR(role, step, ev)                                                            \
   do {                                                                                     \
     if (lcbi_tr != nullptr && (step) < 16) lcbi_tr[((role) * 16 + (step)) * 8 + (ev)] = clock64(); \
@@ -104,33 +97,18 @@ __device__ __forceinline__ long long global_ns() {
 #else
 #define LCBI_TR_INIT() do { } while (0)
 #define LCBI_TR(role, step, ev) do { } while (0)
-#define LCBI_CTA_T(slot) do { } while (0)
+#define LCBI_ITEM_T(slot) do { } while (0)
 #endif
 
 struct BwdParams {
   int B, H, Nq, Nk, Nq_pad;
+  int n_kv_tiles, n_items;
   float scale, scale_log2;
   const __nv_bfloat16* lse_aug;   // (B,H,Nq_pad/64) tiles of kAugBytes: -lse/scale split into bf16 (hi, mid, lo)
   const __nv_bfloat16* d_aug;     // likewise -D, D = rowsum(dO o O)
   float* dq_acc;       // fp32 (B,Nq,H,64) accumulator
   int accumulate_dkv;
 };
-
-#ifndef LCBI_BWD_SETMAXNREG
-#define LCBI_BWD_SETMAXNREG 0
-#endif
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() {
-#if LCBI_BWD_SETMAXNREG
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-#endif
-}
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() {
-#if LCBI_BWD_SETMAXNREG
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-#endif
-}
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -235,36 +213,47 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int kv_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
-  const int kv_base = kv_tile * kTile;
-  const int n_steps = p.Nq_pad / kStep;      // 64-query steps; even because Nq_pad is a multiple of 128
+  const int n_steps = p.Nq_pad / kStep;      // 64-query steps per item; even because Nq_pad is a multiple of 128
+  const int n_tiles = n_steps >> 1;          // 128-query tiles per item
+  const int first_item = blockIdx.x, item_stride = gridDim.x;
   LCBI_TR_INIT();
-#ifdef LCBI_TRACE
-  if (tid == 0) {
-    LCBI_CTA_T(0);
-    if (g_bwd_cta_times != nullptr) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-      g_bwd_cta_times[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 7] = smid;
-    }
-  }
-#endif
 
-  // The TMA warp initialises the barriers and starts the K/V and first Q/dO loads right away, before the CTA-wide
-  // sync below (TMEM allocation, constant tile): measured, K/V reach TMEM ~0.3 us earlier per CTA.
-  const size_t aug_base = (static_cast<size_t>(batch) * p.H + head) * n_steps * (kAugBytes / 2);
-  const int n_prefill = n_steps < kQStages ? n_steps : kQStages;
-  auto load_step = [&](int s) {                // Q_s with its row terms, and dO_s, into ring stage s % kQStages
-    const int st = s % kQStages;
+  // Work item = one 128-key tile of one (batch, head); the kernel is persistent (CTA c takes items c, c + grid, ...).
+  // Adjacent items are adjacent key tiles of one (batch, head), so the CTAs running at any moment stream the same
+  // Q / dO rows (L2 hits). Every ring and barrier phase below derives from counters that run across items:
+  //   gs = it * n_steps + s   (64-query step)       gi = it * n_tiles + i   (128-query tile)
+  auto decode = [&](int item, int& kv_base, int& head, int& batch) {
+    const int kv_tile = item % p.n_kv_tiles, bh = item / p.n_kv_tiles;
+    head = bh % p.H;
+    batch = bh / p.H;
+    kv_base = kv_tile * kTile;
+  };
+  auto load_step = [&](int gs, int s, int head, int batch) {   // Q_s with its row terms, and dO_s, into ring stage gs % 4
+    const int st = gs % kQStages;
+    const size_t aug = ((static_cast<size_t>(batch) * p.H + head) * n_steps + s) * (kAugBytes / 2);
     mbar_expect_tx(&sm.q_full[st], kStepBytes + 2 * kAugBytes);
     tma_load_4d(sm.q[st], &tm_q, &sm.q_full[st], 0, head, s * kStep, batch);
-    bulk_load_1d(sm.lse_aug[st], p.lse_aug + aug_base + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
-    bulk_load_1d(sm.d_aug[st], p.d_aug + aug_base + static_cast<size_t>(s) * (kAugBytes / 2), kAugBytes, &sm.q_full[st]);
+    bulk_load_1d(sm.lse_aug[st], p.lse_aug + aug, kAugBytes, &sm.q_full[st]);
+    bulk_load_1d(sm.d_aug[st], p.d_aug + aug, kAugBytes, &sm.q_full[st]);
     mbar_expect_tx(&sm.do_full[st], kStepBytes);
     tma_load_4d(sm.dout[st], &tm_do, &sm.do_full[st], 0, head, s * kStep, batch);
   };
+  auto load_k = [&](int buf, int kv_base, int head, int batch) {
+    mbar_expect_tx(&sm.k_full[buf], kTileBytes);
+    tma_load_4d(sm.k[buf], &tm_k, &sm.k_full[buf], 0, head, kv_base, batch);
+  };
+  auto load_v = [&](int kv_base, int head, int batch) {
+    mbar_expect_tx(&sm.v_full, kTileBytes);
+    tma_load_4d(sm.v, &tm_v, &sm.v_full, 0, head, kv_base, batch);
+  };
+  const int n_prefill = n_steps < kQStages ? n_steps : kQStages;
+
+  // The TMA warp initialises the barriers and starts the first item's loads right away, before the CTA-wide sync
+  // below (TMEM allocation, constant tile).
   if (warp == 12 && elect_one()) {
-    mbar_init(&sm.kv_full, 1);
+    mbar_init(&sm.k_full[0], 1);
+    mbar_init(&sm.k_full[1], 1);
+    mbar_init(&sm.v_full, 1);
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(&sm.q_full[s], 1);
       mbar_init(&sm.q_empty[s], 1);
@@ -279,11 +268,19 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(&sm.dq_full, 1);
     mbar_init(&sm.dq_empty, 4);        // one arrive per drain warp
     mbar_init(&sm.dkv_full, 1);
+    mbar_init(&sm.dkv_drained, 8);     // one arrive per compute warp
     fence_mbar_init();
-    mbar_expect_tx(&sm.kv_full, 2 * kTileBytes);
-    tma_load_4d(sm.k, &tm_k, &sm.kv_full, 0, head, kv_base, batch);
-    tma_load_4d(sm.v, &tm_v, &sm.kv_full, 0, head, kv_base, batch);
-    for (int s = 0; s < n_prefill; ++s) load_step(s);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    if (first_item < p.n_items) {
+      int kv_base, head, batch;
+      decode(first_item, kv_base, head, batch);
+      load_k(0, kv_base, head, batch);
+      load_v(kv_base, head, batch);
+      for (int s = 0; s < n_prefill; ++s) load_step(s, s, head, batch);
+    }
   }
   if (tid < 2 * kAugBytes / 16) {     // constant A tile of the extra k-step: columns 0-2 = 1.0, the rest 0
     const bool first_half = ((tid >> 3) & 1) == 0;
@@ -301,171 +298,198 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp >= 12) {
-    setmaxnreg_dec<40>();
-    if (warp == 12) {
-      // ---------------------------------------------------------------- TMA producer
-      if (elect_one()) {
+  if (warp == 12) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int it = 0;
+      for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+        int kv_base, head, batch;
+        const int next = item + item_stride;
+        if (next < p.n_items) {
+          // K of the next item goes into the other K buffer right away: its previous tenant (item it-1) retired its
+          // last dQ GEMM before this item started
+          decode(next, kv_base, head, batch);
+          if (it >= 1) mbar_wait(&sm.dkv_full, (it - 1) & 1);
+          load_k((it + 1) & 1, kv_base, head, batch);
+        }
+        decode(item, kv_base, head, batch);
         for (int s = n_prefill; s < n_steps; ++s) {
-          const int st = s % kQStages;
-          const uint32_t ph = (s / kQStages) & 1;
+          const int gs = it * n_steps + s, st = gs % kQStages;
+          const uint32_t ph = (gs / kQStages) & 1;
           mbar_wait(&sm.q_empty[st], ph ^ 1);
           mbar_wait(&sm.do_empty[st], ph ^ 1);
-          load_step(s);
+          load_step(gs, s, head, batch);
+        }
+        if (next < p.n_items) {
+          decode(next, kv_base, head, batch);
+          mbar_wait(&sm.kvt_full, it & 1);     // V of this item has been copied into TMEM: its smem tile is free
+          load_v(kv_base, head, batch);
+          // the next item's first steps: their ring stages free up while this item's last steps retire
+          for (int s = 0; s < n_prefill; ++s) {
+            const int gs = (it + 1) * n_steps + s, st = gs % kQStages;
+            const uint32_t ph = (gs / kQStages) & 1;
+            mbar_wait(&sm.q_empty[st], ph ^ 1);
+            mbar_wait(&sm.do_empty[st], ph ^ 1);
+            load_step(gs, s, head, batch);
+          }
         }
       }
-    } else if (warp == 13) {
-      // ---------------------------------------------------------------- UMMA issuer
-      if (elect_one()) {
-        constexpr uint32_t idesc_nt = make_idesc_bf16(kTile, kStep, 0, 0);       // S^T, dP^T : 128 x 64
-        constexpr uint32_t idesc_kmn = make_idesc_bf16(kTile, kHeadDim, 0, 1);   // dV, dK: A K-major, B MN-major
-        constexpr uint32_t idesc_mnmn = make_idesc_bf16(kTile, kHeadDim, 1, 1);  // dQ: A MN-major, B MN-major
-        // loop-invariant operand descriptors (per k-step only the 14-bit start address field advances)
-        const uint64_t d_k = make_smem_desc(smem_u32(sm.k), 16, 1024, kLayoutSW128);
-        const uint64_t d_q0 = make_smem_desc(smem_u32(sm.q[0]), 16, 1024, kLayoutSW128);      // stages are contiguous
-        const uint64_t d_do0 = make_smem_desc(smem_u32(sm.dout[0]), 16, 1024, kLayoutSW128);
-        const uint64_t d_ds_mn0 = make_smem_desc(smem_u32(sm.ds[0]), kTileBytes, 1024, kLayoutSW128);
-        const uint64_t d_ones = make_smem_desc(smem_u32(sm.ones), kAugLbo, kAugSbo, 0);
-        const uint64_t d_lse0 = make_smem_desc(smem_u32(sm.lse_aug[0]), kAugLbo, kAugSbo, 0);   // stages contiguous
-        const uint64_t d_d0 = make_smem_desc(smem_u32(sm.d_aug[0]), kAugLbo, kAugSbo, 0);
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_nt = make_idesc_bf16(kTile, kStep, 0, 0);       // S^T, dP^T : 128 x 64
+      constexpr uint32_t idesc_kmn = make_idesc_bf16(kTile, kHeadDim, 0, 1);   // dV, dK: A K-major, B MN-major
+      constexpr uint32_t idesc_mnmn = make_idesc_bf16(kTile, kHeadDim, 1, 1);  // dQ: A MN-major, B MN-major
+      // loop-invariant operand descriptors (per k-step only the 14-bit start address field advances)
+      const uint64_t d_k0 = make_smem_desc(smem_u32(sm.k[0]), 16, 1024, kLayoutSW128);        // the two K buffers are contiguous
+      const uint64_t d_q0 = make_smem_desc(smem_u32(sm.q[0]), 16, 1024, kLayoutSW128);      // stages are contiguous
+      const uint64_t d_do0 = make_smem_desc(smem_u32(sm.dout[0]), 16, 1024, kLayoutSW128);
+      const uint64_t d_ds_mn0 = make_smem_desc(smem_u32(sm.ds[0]), kTileBytes, 1024, kLayoutSW128);
+      const uint64_t d_ones = make_smem_desc(smem_u32(sm.ones), kAugLbo, kAugSbo, 0);
+      const uint64_t d_lse0 = make_smem_desc(smem_u32(sm.lse_aug[0]), kAugLbo, kAugSbo, 0);   // stages contiguous
+      const uint64_t d_d0 = make_smem_desc(smem_u32(sm.d_aug[0]), kAugLbo, kAugSbo, 0);
 
-        auto wait_sdp_operands = [&](int s) {   // Q_s (+ row terms) and dO_s have landed
-          mbar_wait(&sm.q_full[s % kQStages], (s / kQStages) & 1);
-          mbar_wait(&sm.do_full[s % kQStages], (s / kQStages) & 1);
-        };
-        auto issue_sdp = [&](int s) {            // S^T(s) = K Q_s^T, dP^T(s) = V dO_s^T into buffer s & 1
-          const int st = s % kQStages, b = s & 1;
-          const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
+      auto wait_sdp_operands = [&](int gs) {   // Q (+ row terms) and dO of step gs have landed
+        mbar_wait(&sm.q_full[gs % kQStages], (gs / kQStages) & 1);
+        mbar_wait(&sm.do_full[gs % kQStages], (gs / kQStages) & 1);
+      };
+      auto issue_sdp = [&](int gs) {           // S^T = K Q^T, dP^T = V dO^T of step gs into buffer gs & 1
+        const int st = gs % kQStages, b = gs & 1;
+        const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
 #pragma unroll
-          for (int kk = 0; kk < ((kAblate & 128) ? 0 : kHeadDim / 16); ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
-            umma_ts(tmem + kTmemS + b * kStep, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt,
-                    kk > 0 ? 1u : 0u);
-          if (!(kAblate & 64)) umma_ss(tmem + kTmemS + b * kStep, d_ones, desc_advance(d_lse0, st * kAugBytes), idesc_nt, 1u);   // - lse/scale
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
+          umma_ts(tmem + kTmemS + b * kStep, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt,
+                  kk > 0 ? 1u : 0u);
+        umma_ss(tmem + kTmemS + b * kStep, d_ones, desc_advance(d_lse0, st * kAugBytes), idesc_nt, 1u);   // - lse/scale
 #pragma unroll
-          for (int kk = 0; kk < ((kAblate & 128) ? 0 : kHeadDim / 16); ++kk)   // A = V from TMEM
-            umma_ts(tmem + kTmemDP + b * kStep, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt,
-                    kk > 0 ? 1u : 0u);
-          if (!(kAblate & 64)) umma_ss(tmem + kTmemDP + b * kStep, d_ones, desc_advance(d_d0, st * kAugBytes), idesc_nt, 1u);    // - D
-          umma_commit(&sm.sdp_full[b]);
-        };
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = V from TMEM
+          umma_ts(tmem + kTmemDP + b * kStep, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt,
+                  kk > 0 ? 1u : 0u);
+        umma_ss(tmem + kTmemDP + b * kStep, d_ones, desc_advance(d_d0, st * kAugBytes), idesc_nt, 1u);    // - D
+        umma_commit(&sm.sdp_full[b]);
+      };
 
-        mbar_wait(&sm.kv_full, 0);
-        mbar_wait(&sm.kvt_full, 0);      // K, V copied into TMEM by the compute warps
-        wait_sdp_operands(0);
+      int it = 0;
+      for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+        const int gs0 = it * n_steps, gi0 = it * n_tiles;
+        const uint64_t d_k = desc_advance(d_k0, (it & 1) * kTileBytes);
+        mbar_wait(&sm.kvt_full, it & 1);     // K, V of this item copied into TMEM by the compute warps
+        wait_sdp_operands(gs0);
         tc_fence_after();
-        issue_sdp(0);
+        issue_sdp(gs0);
         if (n_steps > 1) {
-          wait_sdp_operands(1);
+          wait_sdp_operands(gs0 + 1);
           tc_fence_after();
-          issue_sdp(1);
+          issue_sdp(gs0 + 1);
         }
 
         for (int s = 0; s < n_steps; ++s) {
-          const int st = s % kQStages, b = s & 1, i = s >> 1;
+          const int gs = gs0 + s, st = gs % kQStages, b = gs & 1, gi = gi0 + (s >> 1);
           // every wait that does not depend on the compute warps comes first, so its latency hides behind their work
           // and the GEMMs below go out back to back once P^T / dS^T of the step are ready
-          if (s + 2 < n_steps) wait_sdp_operands(s + 2);
-          if ((s & 1) && !(kAblate & 2)) mbar_wait(&sm.dq_empty, (i & 1) ^ 1);
-          mbar_wait(&sm.pds_full[b], (s >> 1) & 1);
-          LCBI_TR(2, s, 0);
+          if (s + 2 < n_steps) wait_sdp_operands(gs + 2);
+          if (s & 1) mbar_wait(&sm.dq_empty, (gi & 1) ^ 1);
+          if (s == 0 && it > 0) mbar_wait(&sm.dkv_drained, (it - 1) & 1);   // previous item's dV/dK left TMEM
+          mbar_wait(&sm.pds_full[b], (gs >> 1) & 1);
+          if (it == 0) LCBI_TR(2, s, 0);
           tc_fence_after();
           const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
           // dV += P^T(s) dO_s   (A = bf16 P^T, in place in the S buffer: 16 queries = 8 columns per k-step, the
           //                      two 32-query halves start at columns 0 and 32)
 #pragma unroll
-          for (int kk = 0; kk < ((kAblate & 32) ? 0 : kStep / 16); ++kk)
+          for (int kk = 0; kk < kStep / 16; ++kk)
             umma_ts(tmem + kTmemDV, tmem + kTmemS + b * kStep + (kk >> 1) * 32 + (kk & 1) * 8,
                     desc_advance(ddo_s, kk * 2048), idesc_kmn, (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.do_empty[st]);
           // dK += dS^T(s) Q_s   (A = bf16 dS^T, in place in the dP buffer)
 #pragma unroll
-          for (int kk = 0; kk < ((kAblate & 32) ? 0 : kStep / 16); ++kk)
+          for (int kk = 0; kk < kStep / 16; ++kk)
             umma_ts(tmem + kTmemDK, tmem + kTmemDP + b * kStep + (kk >> 1) * 32 + (kk & 1) * 8,
                     desc_advance(dq_s, kk * 2048), idesc_kmn, (s > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&sm.q_empty[st]);
-          LCBI_TR(2, s, 1);
-          if (s + 2 < n_steps) issue_sdp(s + 2);
-          LCBI_TR(2, s, 2);
-          if ((s & 1) && !(kAblate & 2)) {
+          if (it == 0) LCBI_TR(2, s, 1);
+          if (s + 2 < n_steps) issue_sdp(gs + 2);
+          if (it == 0) LCBI_TR(2, s, 2);
+          if (s & 1) {
             // dQ_i = dS(i) K over the whole 128-query tile (A = dS^T read MN-major: both atoms)
-            const uint64_t dds_mn = desc_advance(d_ds_mn0, (i & 1) * 2 * kTileBytes);
+            const uint64_t dds_mn = desc_advance(d_ds_mn0, (gi & 1) * 2 * kTileBytes);
 #pragma unroll
             for (int kk = 0; kk < kTile / 16; ++kk)
               umma_ss(tmem + kTmemDQ, desc_advance(dds_mn, kk * 2048), desc_advance(d_k, kk * 2048), idesc_mnmn,
                       kk > 0 ? 1u : 0u);
             umma_commit(&sm.dq_full);
-            LCBI_TR(2, s, 3);
+            if (it == 0) LCBI_TR(2, s, 3);
           }
         }
         umma_commit(&sm.dkv_full);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ dQ drain (warps 8-11)
-    setmaxnreg_dec<96>();
     const int row = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t t_dq = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kTmemDQ;
     const bool issuer = (tid == 8 * 32);
-    const int n_tiles = (kAblate & 2) ? 0 : (n_steps >> 1);
-    for (int i = 0; i < n_tiles; ++i) {
-      mbar_wait(&sm.dq_full, i & 1);
-      if (issuer) LCBI_TR(3, i, 0);
-      tc_fence_after();
-      uint32_t r[64];
-      tmem_ld_x32(t_dq, r);
-      tmem_ld_x32(t_dq + 32, r + 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.dq_empty);
-      if (kAblate & 8) continue;
-      if constexpr (kDrainWithRed) {
-        // each thread adds its own 256-byte dQ row straight into the fp32 accumulator (16 x red.v4.f32)
-        const int q_row = i * kTile + row;
-        if (q_row < p.Nq) {
-          float* dst = p.dq_acc + ((static_cast<size_t>(batch) * p.Nq + q_row) * p.H + head) * kHeadDim;
+    int it = 0;
+    for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+      int kv_base, head, batch;
+      decode(item, kv_base, head, batch);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int gi = it * n_tiles + i;
+        mbar_wait(&sm.dq_full, gi & 1);
+        if (issuer && it == 0) LCBI_TR(3, i, 0);
+        tc_fence_after();
+        uint32_t r[64];
+        tmem_ld_x32(t_dq, r);
+        tmem_ld_x32(t_dq + 32, r + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.dq_empty);
 #pragma unroll
-          for (int c4 = 0; c4 < 16; ++c4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c4 * 4),
-                         "f"(__uint_as_float(r[c4 * 4]) * p.scale), "f"(__uint_as_float(r[c4 * 4 + 1]) * p.scale),
-                         "f"(__uint_as_float(r[c4 * 4 + 2]) * p.scale), "f"(__uint_as_float(r[c4 * 4 + 3]) * p.scale)
-                         : "memory");
+        for (int half = 0; half < 2; ++half) {    // 32 fp32 columns at a time through the 16 KB staging tile
+          if (issuer) tma_store_wait_read<0>();   // the previous reduce has finished reading the staging tile
+          named_bar_sync(3, 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {           // 16-byte chunk c of the 128-byte fp32 half row (softmax scale folded in)
+            const int e = half * 32 + c * 4;
+            uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[e]) * p.scale),
+                                   __float_as_uint(__uint_as_float(r[e + 1]) * p.scale),
+                                   __float_as_uint(__uint_as_float(r[e + 2]) * p.scale),
+                                   __float_as_uint(__uint_as_float(r[e + 3]) * p.scale));
+            *reinterpret_cast<uint4*>(sm.dq_stage + sw128_offset(row, c)) = val;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(4, 128);
+          if (issuer) {
+            tma_reduce_add_4d(&tm_dqacc, sm.dq_stage, half * 32, head, i * kTile, batch);
+            tma_store_commit();
+          }
         }
-        if (issuer) LCBI_TR(3, i, 1);
-        continue;
-      }
-      if (issuer) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tiles
-      named_bar_sync(3, 128);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {          // 16-byte chunk c of the 256-byte fp32 row (softmax scale folded in)
-        uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[c * 4]) * p.scale),
-                               __float_as_uint(__uint_as_float(r[c * 4 + 1]) * p.scale),
-                               __float_as_uint(__uint_as_float(r[c * 4 + 2]) * p.scale),
-                               __float_as_uint(__uint_as_float(r[c * 4 + 3]) * p.scale));
-        *reinterpret_cast<uint4*>(sm.dq_stage + (c >> 3) * kTileBytes + sw128_offset(row, c & 7)) = val;
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(4, 128);
-      if (issuer) {
-        tma_reduce_add_4d(&tm_dqacc, sm.dq_stage, 0, head, i * kTile, batch);
-        tma_reduce_add_4d(&tm_dqacc, sm.dq_stage + kTileBytes, 32, head, i * kTile, batch);
-        tma_store_commit();
-        LCBI_TR(3, i, 1);
+        if (issuer && it == 0) LCBI_TR(3, i, 1);
       }
     }
     if (issuer) tma_store_wait_read<0>();
-  } else {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ P^T and dS^T in one pass (warps 0-7)
-    setmaxnreg_inc<184>();
     const int hh = warp >> 2;                   // which 32-query half of the 64-query step this thread handles
     const int row = (warp & 3) * 32 + lane;     // key row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c = p.scale_log2;
+    const bool store_issuer = (tid & 127) == 0;
+    bool store_pending = false;                 // the previous item's dV/dK store may still be reading its staging tiles
+    auto finish_store = [&]() {
+      if (store_issuer) tma_store_wait_read<0>();
+      named_bar_sync(7, 256);
+      store_pending = false;
+    };
 
-    // K (warps 0-3) and V (warps 4-7) rows -> TMEM: they are the A operands of every S^T / dP^T GEMM of this CTA
-    {
-      mbar_wait(&sm.kv_full, 0);
-      const uint8_t* src = hh ? sm.v : sm.k;
+    // K (warps 0-3) and V (warps 4-7) rows of item `it_kv` -> TMEM: the A operands of every S^T / dP^T GEMM of that
+    // item. Callers guarantee that the previous item's S^T / dP^T GEMMs have all retired.
+    auto copy_kv_to_tmem = [&](int it_kv) {
+      if (hh) mbar_wait(&sm.v_full, it_kv & 1);
+      else mbar_wait(&sm.k_full[it_kv & 1], (it_kv >> 1) & 1);
+      const uint8_t* src = hh ? sm.v : sm.k[it_kv & 1];
       uint32_t kv[32];
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16) {
@@ -477,111 +501,125 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.kvt_full);
-    }
+    };
 
-    if (tid == 0) LCBI_CTA_T(1);               // K/V are in TMEM
-    for (int s = 0; s < n_steps; ++s) {
-      const int b = s & 1, i = s >> 1;
-      if (tid == 0 && s == 1) LCBI_CTA_T(2);   // first step done
-      if (lane == 0) LCBI_TR(hh, s, 0);
-      // One wait per step: the commit also covers dQ(i-2), the last reader of the dS^T smem buffer.
-      mbar_wait(&sm.sdp_full[b], (s >> 1) & 1);
-      if (lane == 0) LCBI_TR(hh, s, 1);
-      tc_fence_after();
-      if (kAblate & 16) {
+    int it = 0;
+    for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+      int kv_base, head, batch;
+      decode(item, kv_base, head, batch);
+      const int gs0 = it * n_steps, gi0 = it * n_tiles;
+
+      LCBI_ITEM_T(0);
+      if (it == 0) copy_kv_to_tmem(0);           // later items: done at the end of the previous item's last step
+
+      for (int s = 0; s < n_steps; ++s) {
+        const int gs = gs0 + s, b = gs & 1, gi = gi0 + (s >> 1);
+        // the staging tiles of the previous item's dV/dK store live in the dS^T buffer of this item's SECOND tile
+        // (both buffers when the store was an fp32 accumulate): make sure they were read before overwriting them
+        if (s == 1) LCBI_ITEM_T(1);
+        if (s == 2) LCBI_ITEM_T(2);
+        if (store_pending && (s == 2 || p.accumulate_dkv)) finish_store();
+        if (lane == 0 && it == 0) LCBI_TR(hh, s, 0);
+        // One wait per step: the commit also covers dQ of two tiles ago, the last reader of this dS^T smem buffer.
+        mbar_wait(&sm.sdp_full[b], (gs >> 1) & 1);
+        if (lane == 0 && it == 0) LCBI_TR(hh, s, 1);
+        tc_fence_after();
+        uint32_t sv[32], dpv[32];
+        tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + hh * 32, sv);
+        tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
+        tmem_ld_wait();
+        if (lane == 0 && it == 0) LCBI_TR(hh, s, 2);
+        uint32_t pk[16], dsk[16];
+        uint8_t* ds_atom = sm.ds[gi & 1] + (s & 1) * kTileBytes;
+        // the per-query terms were already added by the tensor core: sv = q.k - lse/scale, dpv = dO.v - D
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
+                       "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
+        // in place: the packed results overwrite the first 16 of the 32 columns this thread just read
+        tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + hh * 32, pk);
+        tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dsk);
+        if (lane == 0 && it == 0) LCBI_TR(hh, s, 3);
+        tmem_st_wait();
         tc_fence_before();
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.pds_full[b]);
-        continue;
+        if (lane == 0 && it == 0) LCBI_TR(hh, s, 4);
       }
-      uint32_t sv[32], dpv[32];
-      tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + hh * 32, sv);
-      tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
-      tmem_ld_wait();
-      if (lane == 0) LCBI_TR(hh, s, 2);
-      uint32_t pk[16], dsk[16];
-      uint8_t* ds_atom = sm.ds[i & 1] + (s & 1) * kTileBytes;
-      // the per-query terms were already added by the tensor core: sv = q.k - lse/scale, dpv = dO.v - D
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float p0 = (kAblate & 1) ? __uint_as_float(sv[e]) * c : fast_exp2(__uint_as_float(sv[e]) * c);
-        const float p1 = (kAblate & 1) ? __uint_as_float(sv[e + 1]) * c : fast_exp2(__uint_as_float(sv[e + 1]) * c);
-        pk[e >> 1] = pack_bf16x2(p0, p1);
-        dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
-      }
-#pragma unroll
-      for (int g = 0; g < ((kAblate & 4) ? 0 : 4); ++g)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
-                     "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
-      // in place: the packed results overwrite the first 16 of the 32 columns this thread just read
-      tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + hh * 32, pk);
-      tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dsk);
-      if (lane == 0) LCBI_TR(hh, s, 3);
-      tmem_st_wait();
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.pds_full[b]);
-      if (lane == 0) LCBI_TR(hh, s, 4);
-    }
 
-    // ---- epilogue: warps 0-3 drain dV, warps 4-7 drain dK (scaled)
-    if (tid == 0) LCBI_CTA_T(3);               // last step handed to the tensor core
-    mbar_wait(&sm.dkv_full, 0);
-    if (tid == 0) LCBI_CTA_T(4);               // every GEMM retired
-    tc_fence_after();
-    uint32_t r[64];
-    const uint32_t t_src = tmem + lane_sel + (hh ? kTmemDK : kTmemDV);
-    tmem_ld_x32(t_src, r);
-    tmem_ld_x32(t_src + 32, r + 32);
-    tmem_ld_wait();
-    const float mul = hh ? p.scale : 1.0f;
-    uint8_t* stage = hh ? sm.q[0] : sm.dout[0];   // 32 KB each (all stages), free once every MMA retired
-    const CUtensorMap* tm = hh ? &tm_dk : &tm_dv;
-    if (!p.accumulate_dkv) {
-      // (writing the rows straight from registers with 16-byte st.global was measured: 3.0 us per CTA instead of
-      // 1.6 us for this staged TMA store, the row stride of the qkv layout makes every store a partial sector)
+      // The S^T / dP^T GEMMs of this item have all retired (this thread consumed the last of them), so K and V of the
+      // next item can take their place in TMEM now: its first GEMMs then run while this item's epilogue drains dV / dK.
+      LCBI_ITEM_T(3);
+      if (item + item_stride < p.n_items) copy_kv_to_tmem(it + 1);
+      LCBI_ITEM_T(4);
+
+      // ---- item epilogue: warps 0-3 drain dV, warps 4-7 drain dK (scaled)
+      mbar_wait(&sm.dkv_full, it & 1);          // every GEMM of the item has retired
+      tc_fence_after();
+      uint32_t r[64];
+      const uint32_t t_src = tmem + lane_sel + (hh ? kTmemDK : kTmemDV);
+      tmem_ld_x32(t_src, r);
+      tmem_ld_x32(t_src + 32, r + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      LCBI_ITEM_T(5);
+      if (lane == 0) mbar_arrive(&sm.dkv_drained);   // the next item's first dV / dK GEMM may overwrite TMEM
+      if (store_pending) finish_store();             // (items with fewer than three steps)
+      const float mul = hh ? p.scale : 1.0f;
+      const CUtensorMap* tm = hh ? &tm_dk : &tm_dv;
+      if (!p.accumulate_dkv) {
+        // staging: the dS^T buffer that the NEXT item's first tile does not use (free now, every dQ GEMM has retired)
+        uint8_t* stage = sm.ds[(gi0 + n_tiles + 1) & 1] + hh * kTileBytes;
 #pragma unroll
-      for (int c16 = 0; c16 < 8; ++c16) {
-        uint4 val;
-        val.x = pack_bf16x2(__uint_as_float(r[c16 * 8 + 0]) * mul, __uint_as_float(r[c16 * 8 + 1]) * mul);
-        val.y = pack_bf16x2(__uint_as_float(r[c16 * 8 + 2]) * mul, __uint_as_float(r[c16 * 8 + 3]) * mul);
-        val.z = pack_bf16x2(__uint_as_float(r[c16 * 8 + 4]) * mul, __uint_as_float(r[c16 * 8 + 5]) * mul);
-        val.w = pack_bf16x2(__uint_as_float(r[c16 * 8 + 6]) * mul, __uint_as_float(r[c16 * 8 + 7]) * mul);
-        *reinterpret_cast<uint4*>(stage + sw128_offset(row, c16)) = val;
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(5 + hh, 128);
-      if ((tid & 127) == 0) {
-        tma_store_4d(tm, stage, 0, head, kv_base, batch);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-      }
-    } else {
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint4 val;
+          val.x = pack_bf16x2(__uint_as_float(r[c16 * 8 + 0]) * mul, __uint_as_float(r[c16 * 8 + 1]) * mul);
+          val.y = pack_bf16x2(__uint_as_float(r[c16 * 8 + 2]) * mul, __uint_as_float(r[c16 * 8 + 3]) * mul);
+          val.z = pack_bf16x2(__uint_as_float(r[c16 * 8 + 4]) * mul, __uint_as_float(r[c16 * 8 + 5]) * mul);
+          val.w = pack_bf16x2(__uint_as_float(r[c16 * 8 + 6]) * mul, __uint_as_float(r[c16 * 8 + 7]) * mul);
+          *reinterpret_cast<uint4*>(stage + sw128_offset(row, c16)) = val;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(5 + hh, 128);
+        if (store_issuer) {
+          tma_store_4d(tm, stage, 0, head, kv_base, batch);
+          tma_store_commit();
+        }
+      } else {
+        uint8_t* stage = sm.ds[hh];              // fp32: two [128 x 32] tiles per matrix
 #pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[cc * 4]) * mul),
-                               __float_as_uint(__uint_as_float(r[cc * 4 + 1]) * mul),
-                               __float_as_uint(__uint_as_float(r[cc * 4 + 2]) * mul),
-                               __float_as_uint(__uint_as_float(r[cc * 4 + 3]) * mul));
-        *reinterpret_cast<uint4*>(stage + (cc >> 3) * kTileBytes + sw128_offset(row, cc & 7)) = val;
+        for (int cc = 0; cc < 16; ++cc) {
+          uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[cc * 4]) * mul),
+                                 __float_as_uint(__uint_as_float(r[cc * 4 + 1]) * mul),
+                                 __float_as_uint(__uint_as_float(r[cc * 4 + 2]) * mul),
+                                 __float_as_uint(__uint_as_float(r[cc * 4 + 3]) * mul));
+          *reinterpret_cast<uint4*>(stage + (cc >> 3) * kTileBytes + sw128_offset(row, cc & 7)) = val;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(5 + hh, 128);
+        if (store_issuer) {
+          tma_reduce_add_4d(tm, stage, 0, head, kv_base, batch);
+          tma_reduce_add_4d(tm, stage + kTileBytes, 32, head, kv_base, batch);
+          tma_store_commit();
+        }
       }
-      fence_proxy_async_smem();
-      named_bar_sync(5 + hh, 128);
-      if ((tid & 127) == 0) {
-        tma_reduce_add_4d(tm, stage, 0, head, kv_base, batch);
-        tma_reduce_add_4d(tm, stage + kTileBytes, 32, head, kv_base, batch);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-      }
+      store_pending = true;
+      LCBI_ITEM_T(6);
     }
+    if (store_pending && store_issuer) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) LCBI_CTA_T(5);
   if (warp == 13) tmem_dealloc(tmem, 512);
-  if (tid == 0) LCBI_CTA_T(6);
 }
 
 int make_bf16_map(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t* st, int box_rows = kTile) {
@@ -611,8 +649,8 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 extern "C" int lcbi_debug_set_bwd_trace(long long* ptr) {
   return static_cast<int>(cudaMemcpyToSymbol(g_bwd_trace, &ptr, sizeof(ptr)));
 }
-extern "C" int lcbi_debug_set_bwd_cta_times(long long* ptr) {
-  return static_cast<int>(cudaMemcpyToSymbol(g_bwd_cta_times, &ptr, sizeof(ptr)));
+extern "C" int lcbi_debug_set_bwd_item_times(long long* ptr) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_bwd_item_times, &ptr, sizeof(ptr)));
 }
 #endif
 
@@ -691,7 +729,16 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   p.d_aug = reinterpret_cast<const __nv_bfloat16*>(d_aug);
   p.dq_acc = dq_acc;
   p.accumulate_dkv = a.accumulate_dkv;
-  dim3 grid((a.Nk + kTile - 1) / kTile, a.H, a.B);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  p.n_kv_tiles = (a.Nk + kTile - 1) / kTile;
+  p.n_items = p.n_kv_tiles * a.H * a.B;
+  dim3 grid(p.n_items < num_sms ? p.n_items : num_sms);
   dense_attn_bwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, tdo, tacc, tdk, tdv, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);

@@ -75,7 +75,7 @@ struct FwdParams {
 };
 
 // Timing-only ablations (results become wrong; every barrier still fires): bit 0 no exp2, bit 1 no row-max pass,
-// bit 2 softmax warps only wait and arrive.
+// bit 2 softmax warps only wait and arrive, bit 3 bf16 packing by truncation (one PRMT) instead of F2FP.
 #ifndef LCBI_FWD_ABLATE
 #define LCBI_FWD_ABLATE 0
 #endif
@@ -303,8 +303,8 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const float e2 = ex(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
           const float e3 = ex(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
           s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-          pk[i / 2] = pack_bf16x2(e0, e1);
-          pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+          pk[i / 2] = (kAblate & 8) ? __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632) : pack_bf16x2(e0, e1);
+          pk[i / 2 + 1] = (kAblate & 8) ? __byte_perm(__float_as_uint(e2), __float_as_uint(e3), 0x7632) : pack_bf16x2(e2, e3);
         }
         l += (s0 + s1) + (s2 + s3);
         if (row == 0) LCBI_TR(0, j, 4);

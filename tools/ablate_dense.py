@@ -13,8 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CSRC = os.path.join(ROOT, "long_context_biomedical_imaging_b200", "csrc")
-BWD_MASKS = [int(x) for x in os.environ.get("ABL_BWD", "0,1,2,4,8,16,6,7").split(",") if x != ""]
-FWD_MASKS = [int(x) for x in os.environ.get("ABL_FWD", "").split(",") if x != ""]
+BWD_MASKS = [int(x) for x in os.environ.get("ABL_BWD", "").split(",") if x != ""]   # backward switches existed up to commit a07535e
+FWD_MASKS = [int(x) for x in os.environ.get("ABL_FWD", "0,1,2,3,4").split(",") if x != ""]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-lineinfo", "-Xcompiler", "-fPIC"]
 OTHERS = ["capi", "dense_attn_fwd", "dense_attn_bwd", "window_attn", "window_attn_small", "patch_embed", "attn_merge"]
 

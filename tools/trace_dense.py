@@ -38,33 +38,33 @@ if __name__ == "__main__":
     assert lib.lcbi_debug_set_fwd_trace(ctypes.c_void_p(trace.data_ptr())) == 0
     ops.dense_attn_fwd(q, k, v, 0.125)
     torch.cuda.synchronize()
-    if os.environ.get("TR_CTA"):
-        # per-CTA wall-clock phases of the backward kernel (globaltimer) and the gaps between CTAs on one SM
+    if os.environ.get("TR_ITEMS"):
+        # wall-clock phases (globaltimer, compute thread 0) of every item of every persistent backward CTA
         o, lse = ops.dense_attn_fwd(q, k, v, 0.125)
         d_o = torch.randn_like(o)
         for _ in range(2):
             ops.dense_attn_bwd(q, k, v, o, d_o, lse, 0.125)
-        n_cta = B * H * ((N + 127) // 128)
-        ct = torch.zeros(n_cta * 8, dtype=torch.int64, device="cuda")
-        lib.lcbi_debug_set_bwd_cta_times.argtypes = [ctypes.c_void_p]
-        assert lib.lcbi_debug_set_bwd_cta_times(ctypes.c_void_p(ct.data_ptr())) == 0
+        n_cta = 148
+        ct = torch.zeros(n_cta * 32 * 8, dtype=torch.int64, device="cuda")
+        lib.lcbi_debug_set_bwd_item_times.argtypes = [ctypes.c_void_p]
+        assert lib.lcbi_debug_set_bwd_item_times(ctypes.c_void_p(ct.data_ptr())) == 0
         ops.dense_attn_bwd(q, k, v, o, d_o, lse, 0.125)
         torch.cuda.synchronize()
-        t = ct.cpu().view(n_cta, 8).double()
-        names = ["start->kv in tmem", "->first step done", "->last step issued", "->all gemms retired", "->epilogue done", "->dealloc"]
+        t = ct.cpu().view(n_cta, 32, 8).double()
+        valid = t[:, :, 0] > 0
+        names = ["item start -> step 1", "step 1 -> step 2", "step 2 -> last step done", "copy next K/V to TMEM", "wait all GEMMs retired",
+                 "read dV/dK + stage + store"]
         for i, nm in enumerate(names):
-            d = t[:, i + 1] - t[:, i]
-            print(f"{nm:24s} mean {d.mean():8.0f} ns  median {d.median():8.0f}  p90 {d.quantile(0.9):8.0f}")
-        tot = t[:, 6] - t[:, 0]
-        print(f"CTA lifetime             mean {tot.mean():8.0f} ns  median {tot.median():8.0f}")
-        gaps = []
-        for sm_id in t[:, 7].unique():
-            rows = t[t[:, 7] == sm_id]
-            rows = rows[rows[:, 0].argsort()]
-            gaps.append(rows[1:, 0] - rows[:-1, 6])
-        g = torch.cat(gaps)
-        print(f"gap exit->next start     mean {g.mean():8.0f} ns  median {g.median():8.0f}  p90 {g.quantile(0.9):8.0f}  (n={len(g)})")
-        print(f"kernel span {t[:, 6].max() - t[:, 0].min():.0f} ns, CTAs per SM max {max(int((t[:, 7] == x).sum()) for x in t[:, 7].unique())}")
+            d = (t[:, :, i + 1] - t[:, :, i])[valid]
+            print(f"{nm:28s} mean {d.mean():8.0f} ns  median {d.median():8.0f}  p90 {d.quantile(0.9):8.0f}")
+        tot = (t[:, :, 6] - t[:, :, 0])[valid]
+        print(f"item total                   mean {tot.mean():8.0f} ns  median {tot.median():8.0f}  items {int(valid.sum())}")
+        nxt = (t[:, 1:, 0] - t[:, :-1, 6])[valid[:, 1:]]
+        print(f"store issue -> next start    mean {nxt.mean():8.0f} ns")
+        first = t[:, 0, 0][valid[:, 0]]
+        last = t[:, :, 6].max(dim=1).values
+        print(f"first item starts spread {first.max() - first.min():.0f} ns; CTA busy span mean {(last - t[:, 0, 0]).mean():.0f} max {(last - t[:, 0, 0]).max():.0f} ns")
+        print("CTA 0 items:", [int(x) for x in (t[0, :, 6] - t[0, :, 0])[valid[0]]])
         sys.exit(0)
     if os.environ.get("TR_BWD"):
         o, lse = ops.dense_attn_fwd(q, k, v, 0.125)
