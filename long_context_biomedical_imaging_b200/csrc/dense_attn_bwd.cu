@@ -5,27 +5,32 @@
 // recomputed per tile from q, k and the forward's log-sum-exp, nothing N x N is stored.
 //
 // Three launches:
-//   bwd_prep      D[b,h,i] = sum_d dO*O ; lse2 = lse*log2(e) (rows padded to the 128-row tile get +inf / 0)
-//   bwd_main      one CTA = one 128-key tile of one (batch, head); loops over 128-row query tiles.
-//                 dK, dV accumulate in TMEM over the loop; each tile's dQ partial is reduced into an fp32
-//                 accumulator with a TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32).
-//   bwd_finish    dq = bf16(scale * dq_accum)
+//   bwd_prep      per query row: a = -lse/scale and b = -D, D = sum_d dO*O, each split into three bf16 parts (hi, mid,
+//                 lo) and laid out as [64 x 16] UMMA operand tiles; zeroes the fp32 dQ accumulator
+//   bwd_main      persistent; work item = one 128-key tile of one (batch, head), looping over 64-query steps.
+//                 dK, dV accumulate in TMEM over an item; each 128-query tile's dQ partial is reduced into an fp32
+//                 accumulator with TMA reduce-adds (cp.reduce.async.bulk.tensor .add.f32).
+//   bwd_finish    dq = bf16(dq_accum)
 //
-// bwd_main pipelines 64-QUERY steps s (two per 128-query tile i); all five GEMMs run on tcgen05 with accumulators
-// in TMEM, in a transposed formulation so that the exponentiating threads own KEY rows and P^T / dS^T come out in
-// the layout the next GEMM wants. S^T, dP^T and P^T are double-buffered in TMEM, so the tensor core computes step
-// s+1's S^T / dP^T while the compute warps work on step s:
-//   S^T(s)  = K  Q_s^T     A = K  (smem, K-major)       B = Q_s  (smem, K-major)   -> TMEM [0,128)   (2 x 64)
-//   dP^T(s) = V  dO_s^T    A = V  (smem, K-major)       B = dO_s (smem, K-major)   -> TMEM [128,256) (2 x 64)
-//   one fused pass per step (warps 0-7, thread = key row x 32 query columns):
-//       P^T  = exp2(S^T*c - lse2[q])      -> bf16 -> TMEM [448,512) (2 x 32)
-//       dS^T = P^T o (dP^T - D[q])        -> bf16 -> swizzled smem atom of this step
-//   dV  += P^T(s)  dO_s    A = P^T (TMEM)               B = dO_s (smem, MN-major)  -> TMEM [256,320)
-//   dK  += dS^T(s) Q_s     A = dS^T atom (smem, K-major) B = Q_s (smem, MN-major)  -> TMEM [320,384)
-//   every second step:  dQ_i = dS(i) K   A = both dS^T atoms read MN-major, B = K (MN-major) -> TMEM [384,448)
+// bwd_main: all five GEMMs run on tcgen05 with accumulators in TMEM, in a transposed formulation so that the
+// exponentiating threads own KEY rows and P^T / dS^T come out in the layout the next GEMM wants. K and V sit in TMEM
+// as A operands; S^T and dP^T are double-buffered in TMEM, so the tensor core computes step s+2's S^T / dP^T while
+// the compute warps work on step s+1:
+//   S^T(s)  = K Q_s^T  - lse/scale    A = K  (TMEM)   B = Q_s  (smem, K-major)  + one K=16 step: A = (1,1,1,0..) tile,
+//   dP^T(s) = V dO_s^T - D            A = V  (TMEM)   B = dO_s (smem, K-major)    B = the step's (hi, mid, lo) tile
+//   one fused pass per step (warps 0-7, thread = key row x 32 query columns), no per-query loads needed:
+//       P^T  = exp2(S^T * scale*log2e)   -> bf16 -> in place over the first half of the S^T columns it came from
+//       dS^T = P^T o dP^T                -> bf16 -> in place over dP^T, and into the swizzled dS^T smem tile
+//   dV  += P^T(s)  dO_s    A = P^T  (TMEM)   B = dO_s (smem, MN-major)   -> TMEM [256,320)
+//   dK  += dS^T(s) Q_s     A = dS^T (TMEM)   B = Q_s  (smem, MN-major)   -> TMEM [320,384)
+//   every second step:  dQ_i = dS(i) K   A = both dS^T smem atoms read MN-major, B = K (smem, MN-major) -> [384,448)
 // Warp roles (512 threads): warps 0-7 compute, warps 8-11 drain dQ_i (TMEM -> x scale -> swizzled fp32 smem -> TMA
-// reduce-add), warp 12 TMA producer (Q/dO/lse2/D through 4-stage rings), warp 13 UMMA issuer (operand descriptors
-// are built once; only the start-address field advances per k-step).
+// reduce-add, 32 columns at a time), warp 12 TMA producer (Q / dO / row-term tiles through 4-stage rings that run
+// across items, K double-buffered across items, V), warp 13 UMMA issuer (operand descriptors are built once; only
+// the start-address field advances), warps 14-15 idle.
+// Item transitions overlap: K(next) is prefetched during the item, V(next) follows once V has been copied to TMEM,
+// the compute warps move K/V(next) into TMEM right after their last step, so S^T / dP^T of the next item run while
+// dV / dK of this one are drained (TMEM -> bf16 -> the idle dS^T smem buffer -> TMA store).
 #include "lcbi_kernels.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
@@ -120,7 +125,8 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 // ------------------------------------------------------------------------------------------------
 // prep: per query row the two terms the main kernel adds through its extra k-step, a = -lse/scale and b = -D with
-// D = rowsum(dO o O), each split into three bf16 parts and written in the operand tile layout; 8 threads per row
+// D = rowsum(dO o O), each split into three bf16 parts and written in the operand tile layout; 8 threads per row.
+// Also zeroes the fp32 dQ accumulator (unless the caller accumulates into its own), saving a memset launch.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 split3_bf16(float x) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(x);
@@ -137,7 +143,8 @@ __device__ __forceinline__ uint4 split3_bf16(float x) {
 
 __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                 const float* __restrict__ lse, uint8_t* __restrict__ lse_aug,
-                                uint8_t* __restrict__ d_aug, float inv_scale, int B, int H, int Nq, int Nq_pad,
+                                uint8_t* __restrict__ d_aug, float* __restrict__ dq_acc_to_zero, float inv_scale, int B,
+                                int H, int Nq, int Nq_pad,
                                 int64_t o_sb, int64_t o_sr, int64_t o_sh, int64_t do_sb, int64_t do_sr, int64_t do_sh) {
   // 8 threads per (b, h, row): each loads 16 bytes of O and dO; rows ordered (b, row, h) so that a warp's four
   // rows are adjacent heads of one token (contiguous 512 bytes in the usual (B,N,H,d) layout)
@@ -152,6 +159,11 @@ __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_
   const int64_t chunk0 = tile * kAugBytes + aug_chunk_offset(row % kStep, 0);
   float acc = 0.f;
   if (row < Nq) {
+    if (dq_acc_to_zero != nullptr) {   // the fp32 dQ accumulator row of (b, row, h): 256 bytes, 32 per thread
+      float4* z = reinterpret_cast<float4*>(dq_acc_to_zero + ((static_cast<int64_t>(b) * Nq + row) * H + h) * kHeadDim) + sub * 2;
+      z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const uint4 ov = *reinterpret_cast<const uint4*>(o + b * o_sb + row * o_sr + h * o_sh + sub * 8);
     const uint4 dv = *reinterpret_cast<const uint4*>(d_o + b * do_sb + row * do_sr + h * do_sh + sub * 8);
     const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
@@ -698,17 +710,13 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   }
 
   cudaError_t e = cudaSuccess;
-  if (!a.accumulate_dq) {
-    e = cudaMemsetAsync(dq_acc, 0, acc_bytes, stream);
-    if (e != cudaSuccess) return set_cuda_error(e);
-  }
   {
     const int64_t rows = static_cast<int64_t>(a.B) * a.H * nq_pad;
     const int threads = 256;
     const int64_t blocks = (rows * 8 + threads - 1) / threads;
     bwd_prep_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(a.o), reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.lse, lse_aug, d_aug,
-        1.0f / a.scale, a.B, a.H, a.Nq, nq_pad, a.o_strides[0], a.o_strides[1], a.o_strides[2], a.do_strides[0], a.do_strides[1],
+        a.accumulate_dq ? nullptr : dq_acc, 1.0f / a.scale, a.B, a.H, a.Nq, nq_pad, a.o_strides[0], a.o_strides[1], a.o_strides[2], a.do_strides[0], a.do_strides[1],
         a.do_strides[2]);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
