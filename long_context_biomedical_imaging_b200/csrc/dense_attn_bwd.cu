@@ -25,7 +25,7 @@
 //   dK  += dS^T(s) Q_s     A = dS^T (TMEM)   B = Q_s  (smem, MN-major)   -> TMEM [320,384)
 //   every second step:  dQ_i = dS(i) K   A = both dS^T smem atoms read MN-major, B = K (smem, MN-major) -> [384,448)
 // Warp roles (512 threads): warps 0-7 compute, warps 8-11 drain dQ_i (TMEM -> x scale -> swizzled fp32 smem -> TMA
-// reduce-add, 32 columns at a time), warp 12 TMA producer (Q / dO / row-term tiles through 4-stage rings that run
+// reduce-add), warp 12 TMA producer (Q / dO / row-term tiles through 4-stage rings that run
 // across items, K double-buffered across items, V), warp 13 UMMA issuer (operand descriptors are built once; only
 // the start-address field advances), warps 14-15 idle.
 // Item transitions overlap: K(next) is prefetched during the item, V(next) follows once V has been copied to TMEM,
@@ -51,11 +51,12 @@ constexpr int kQStages = 4;
 // Per-query row terms ride along as one extra K=16 step of the S^T / dP^T GEMMs: the fp32 value is split into three
 // bf16 parts (hi, mid, lo) stored in columns 0-2 of a [64 queries x 16] K-major tile, multiplied by a constant
 // [128 keys x 16] tile holding (1, 1, 1, 0, ...). Tiles use the un-swizzled canonical layout: 8-row x 16-byte core
-// matrices, the two 16-byte k-halves of a row group 128 bytes apart (LBO), row groups 256 bytes apart (SBO).
-constexpr int kAugBytes = kStep * 16 * 2;          // 2 KB
-constexpr uint32_t kAugLbo = 128, kAugSbo = 256;
-__host__ __device__ constexpr int aug_chunk_offset(int row, int khalf) {   // byte offset of a 16-byte chunk
-  return (row >> 3) * static_cast<int>(kAugSbo) + khalf * static_cast<int>(kAugLbo) + (row & 7) * 16;
+// matrices 128 bytes apart (SBO). Only the first 16-byte k-half of a row carries data; the second k-half of EVERY
+// tile is one shared block of zeros, reached through the descriptor's leading byte offset (LBO = zeros - tile).
+constexpr int kAugBytes = kStep * 16;              // 1 KB: [64 rows x 8 bf16]
+constexpr uint32_t kAugSbo = 128;
+__host__ __device__ constexpr int aug_chunk_offset(int row) {   // byte offset of a row's 16-byte chunk
+  return (row >> 3) * static_cast<int>(kAugSbo) + (row & 7) * 16;
 }
 
 // TMEM columns: S^T and dP^T are double-buffered per 64-query step; the bf16 P^T / dS^T of a step overwrite, in
@@ -70,10 +71,11 @@ struct __align__(1024) BwdSmem {
   uint8_t q[kQStages][kStepBytes];      // 64-query tiles; together also the dK staging area of the epilogue
   uint8_t dout[kQStages][kStepBytes];   // likewise dV staging
   uint8_t ds[2][2 * kTileBytes];        // dS^T per 128-query tile (double-buffered): two [128 keys x 64 queries] atoms
-  uint8_t dq_stage[kTileBytes];         // one [128 queries x 32 fp32] SW128 tile (a dQ tile goes out in two halves)
+  uint8_t dq_stage[2 * kTileBytes];     // two [128 queries x 32 fp32] SW128 tiles
   uint8_t lse_aug[kQStages][kAugBytes];   // per-query -lse/scale as the B operand of one extra k-step of S^T
   uint8_t d_aug[kQStages][kAugBytes];     // per-query -D likewise for dP^T
-  uint8_t ones[2 * kAugBytes];            // [128 keys x 16] constant A operand of those k-steps: (1, 1, 1, 0, ...)
+  uint8_t ones[2 * kAugBytes];            // [128 keys x 8] constant A operand of those k-steps: (1, 1, 1, 0, ...)
+  uint8_t aug_zeros[2 * kAugBytes];       // second k-half of every row-term tile (placed after them: LBO > 0)
   uint64_t k_full[2], v_full;
   uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
   uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full, dkv_drained;
@@ -156,7 +158,7 @@ __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_
   const int row = static_cast<int>((r / H) % Nq_pad);
   const int b = static_cast<int>(r / (static_cast<int64_t>(H) * Nq_pad));
   const int64_t tile = (static_cast<int64_t>(b) * H + h) * (Nq_pad / kStep) + row / kStep;
-  const int64_t chunk0 = tile * kAugBytes + aug_chunk_offset(row % kStep, 0);
+  const int64_t chunk0 = tile * kAugBytes + aug_chunk_offset(row % kStep);
   float acc = 0.f;
   if (row < Nq) {
     if (dq_acc_to_zero != nullptr) {   // the fp32 dQ accumulator row of (b, row, h): 256 bytes, 32 per thread
@@ -183,9 +185,6 @@ __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_
     const float a = row < Nq ? -lse[(static_cast<int64_t>(b) * H + h) * Nq + row] * inv_scale : -1e30f;
     *reinterpret_cast<uint4*>(lse_aug + chunk0) = split3_bf16(a);
     *reinterpret_cast<uint4*>(d_aug + chunk0) = split3_bf16(-acc);
-  } else if (sub == 1) {
-    *reinterpret_cast<uint4*>(lse_aug + chunk0 + kAugLbo) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(d_aug + chunk0 + kAugLbo) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -294,10 +293,9 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       for (int s = 0; s < n_prefill; ++s) load_step(s, s, head, batch);
     }
   }
-  if (tid < 2 * kAugBytes / 16) {     // constant A tile of the extra k-step: columns 0-2 = 1.0, the rest 0
-    const bool first_half = ((tid >> 3) & 1) == 0;
-    *reinterpret_cast<uint4*>(sm.ones + tid * 16) =
-        first_half ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 2 * kAugBytes / 16) {     // constant A tile of the extra k-step (columns 0-2 = 1.0) and the shared zeros
+    *reinterpret_cast<uint4*>(sm.ones + tid * 16) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sm.aug_zeros + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
   __syncwarp();
@@ -358,9 +356,17 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const uint64_t d_q0 = make_smem_desc(smem_u32(sm.q[0]), 16, 1024, kLayoutSW128);      // stages are contiguous
       const uint64_t d_do0 = make_smem_desc(smem_u32(sm.dout[0]), 16, 1024, kLayoutSW128);
       const uint64_t d_ds_mn0 = make_smem_desc(smem_u32(sm.ds[0]), kTileBytes, 1024, kLayoutSW128);
-      const uint64_t d_ones = make_smem_desc(smem_u32(sm.ones), kAugLbo, kAugSbo, 0);
-      const uint64_t d_lse0 = make_smem_desc(smem_u32(sm.lse_aug[0]), kAugLbo, kAugSbo, 0);   // stages contiguous
-      const uint64_t d_d0 = make_smem_desc(smem_u32(sm.d_aug[0]), kAugLbo, kAugSbo, 0);
+      const uint32_t zeros_addr = smem_u32(sm.aug_zeros);
+      auto aug_desc = [&](const void* tile) {     // k-half 0 in the tile, k-half 1 = the shared zeros
+        return make_smem_desc(smem_u32(tile), zeros_addr - smem_u32(tile), kAugSbo, 0);
+      };
+      const uint64_t d_ones = aug_desc(sm.ones);
+      const uint64_t d_lse0 = aug_desc(sm.lse_aug[0]), d_d0 = aug_desc(sm.d_aug[0]);   // stages are contiguous
+      // stage st: the start address moves up by st KB and the distance to the zeros shrinks by as much
+      auto aug_stage = [](uint64_t d0, int st) {
+        const uint64_t step = static_cast<uint64_t>(st) * (kAugBytes >> 4);
+        return d0 + step - (step << 16);
+      };
 
       auto wait_sdp_operands = [&](int gs) {   // Q (+ row terms) and dO of step gs have landed
         mbar_wait(&sm.q_full[gs % kQStages], (gs / kQStages) & 1);
@@ -373,12 +379,12 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = K from TMEM (8 packed columns per 16-wide k-step)
           umma_ts(tmem + kTmemS + b * kStep, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt,
                   kk > 0 ? 1u : 0u);
-        umma_ss(tmem + kTmemS + b * kStep, d_ones, desc_advance(d_lse0, st * kAugBytes), idesc_nt, 1u);   // - lse/scale
+        umma_ss(tmem + kTmemS + b * kStep, d_ones, aug_stage(d_lse0, st), idesc_nt, 1u);   // - lse/scale
 #pragma unroll
         for (int kk = 0; kk < kHeadDim / 16; ++kk)   // A = V from TMEM
           umma_ts(tmem + kTmemDP + b * kStep, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt,
                   kk > 0 ? 1u : 0u);
-        umma_ss(tmem + kTmemDP + b * kStep, d_ones, desc_advance(d_d0, st * kAugBytes), idesc_nt, 1u);    // - D
+        umma_ss(tmem + kTmemDP + b * kStep, d_ones, aug_stage(d_d0, st), idesc_nt, 1u);    // - D
         umma_commit(&sm.sdp_full[b]);
       };
 
@@ -458,25 +464,22 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.dq_empty);
+        if (issuer) tma_store_wait_read<0>();   // the previous reduce has finished reading the staging tiles
+        named_bar_sync(3, 128);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {    // 32 fp32 columns at a time through the 16 KB staging tile
-          if (issuer) tma_store_wait_read<0>();   // the previous reduce has finished reading the staging tile
-          named_bar_sync(3, 128);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {           // 16-byte chunk c of the 128-byte fp32 half row (softmax scale folded in)
-            const int e = half * 32 + c * 4;
-            uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[e]) * p.scale),
-                                   __float_as_uint(__uint_as_float(r[e + 1]) * p.scale),
-                                   __float_as_uint(__uint_as_float(r[e + 2]) * p.scale),
-                                   __float_as_uint(__uint_as_float(r[e + 3]) * p.scale));
-            *reinterpret_cast<uint4*>(sm.dq_stage + sw128_offset(row, c)) = val;
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(4, 128);
-          if (issuer) {
-            tma_reduce_add_4d(&tm_dqacc, sm.dq_stage, half * 32, head, i * kTile, batch);
-            tma_store_commit();
-          }
+        for (int c = 0; c < 16; ++c) {          // 16-byte chunk c of the 256-byte fp32 row (softmax scale folded in)
+          uint4 val = make_uint4(__float_as_uint(__uint_as_float(r[c * 4]) * p.scale),
+                                 __float_as_uint(__uint_as_float(r[c * 4 + 1]) * p.scale),
+                                 __float_as_uint(__uint_as_float(r[c * 4 + 2]) * p.scale),
+                                 __float_as_uint(__uint_as_float(r[c * 4 + 3]) * p.scale));
+          *reinterpret_cast<uint4*>(sm.dq_stage + (c >> 3) * kTileBytes + sw128_offset(row, c & 7)) = val;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(4, 128);
+        if (issuer) {
+          tma_reduce_add_4d(&tm_dqacc, sm.dq_stage, 0, head, i * kTile, batch);
+          tma_reduce_add_4d(&tm_dqacc, sm.dq_stage + kTileBytes, 32, head, i * kTile, batch);
+          tma_store_commit();
         }
         if (issuer && it == 0) LCBI_TR(3, i, 1);
       }
