@@ -45,6 +45,16 @@ int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, con
                            float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
                            const int* patch, const int* grid, int N, cudaStream_t stream);
 
+// tensor-core variants for K >= 64 at fp32 accuracy (patch_embed_mma.cu); `applicable` is a host-side shape test
+bool patch_embed_mma_applicable(int Cin, const int* img_dims, const int* patch, const int* grid, int N);
+int patch_embed_fwd_mma_launch(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
+                               void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
+                               const int* grid, int N, cudaStream_t stream);
+
+int patch_embed_bwd_w_mma_launch(const void* img, int img_is_bf16, const void* dout, int dout_is_bf16, float* dw,
+                                 float* dbias, int B, int Cin, const int* img_dims, const int* patch, const int* grid,
+                                 int N, cudaStream_t stream);
+
 // Swin window attention (window_attn.cu)
 struct WinAttnArgs {
   int ndim;                       // 2 or 3

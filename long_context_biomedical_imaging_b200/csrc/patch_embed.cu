@@ -365,6 +365,9 @@ int patch_embed_fwd_launch(const void* img, int img_is_bf16, const float* w, con
   PEGeom g;
   int rc = fill_geom(g, img_dims, patch, grid, B, Cin, N);
   if (rc) return rc;
+  if (patch_embed_mma_applicable(Cin, img_dims, patch, grid, N))
+    return patch_embed_fwd_mma_launch(img, img_is_bf16, w, bias, pos, out, out_is_bf16, B, Cin, img_dims, patch, grid, N,
+                                      stream);
   dim3 grd(static_cast<unsigned>((g.M + TM - 1) / TM), (N + TN - 1) / TN);
 #define LCBI_PE_FWD(TI, TO) \
   patch_embed_fwd_kernel<TI, TO><<<grd, kThreads, 0, stream>>>(static_cast<const TI*>(img), w, bias, pos, \
@@ -418,6 +421,10 @@ int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, con
       if (dout_is_bf16) LCBI_PE_BSK(float, __nv_bfloat16); else LCBI_PE_BSK(float, float);
     }
 #undef LCBI_PE_BSK
+  } else if (patch_embed_mma_applicable(Cin, img_dims, patch, grid, N)) {
+    rc = patch_embed_bwd_w_mma_launch(img, img_is_bf16, dout, dout_is_bf16, dw, dbias, B, Cin, img_dims, patch, grid, N,
+                                      stream);
+    if (rc) return rc;
   } else {
     dim3 grd(static_cast<unsigned>((g.M + MS - 1) / MS), (N + TN - 1) / TN, (g.K + KC - 1) / KC);
 #define LCBI_PE_BWD(TI, TG) \

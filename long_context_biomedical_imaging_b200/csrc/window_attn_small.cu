@@ -271,7 +271,6 @@ struct SmallBwdSmem {
   static constexpr int kStride = Tile<D>::kStride;
   static constexpr int kTileBytes = 64 * kStride;
   static constexpr int kPBytes = 64 * kPStride;
-  static constexpr int kTabFloats = 2200;   // >= prod(2*window-1) for every window with <= 64 tokens... checked on host
   static constexpr int kTotal = 4 * kTileBytes + 2 * kPBytes + 2 * 64 * 4 /*lse, dsum*/ + 4 * 64 * 4 /*meta*/;
 };
 

@@ -135,6 +135,43 @@ def test_patch_embed_vs_golden():
             assert max_rel(pos.grad.cpu(), g[f"{name}/dpos"]) < FP32_TOL, name
 
 
+@pytest.mark.parametrize("shape", [
+    # (B, Cin, image dims, patch, hidden): K = Cin * prod(patch) >= 64 and % 32 == 0 -> split-bf16 tensor-core kernels
+    (2, 1, (1, 48, 80), (1, 16, 16), 192),      # cfg1-like, K = 256, M = 30 (ragged tile)
+    (3, 1, (16, 24, 40), (8, 8, 8), 200),       # cfg3-like, K = 512, N not a multiple of 128
+    (2, 3, (1, 20, 24), (1, 4, 8), 72),         # K = 96: three 32-chunks, partial 128-wide k tile in the backward
+])
+def test_patch_embed_large_k_tensor_core_path_fp32_accuracy(shape):
+    """The K >= 64 path multiplies hi/lo bf16 splits on the tensor cores; it must still meet the fp32 tolerance
+    against torch's fp32 strided convolution (the MONAI PatchEmbeddingBlock semantics)."""
+    import torch.nn.functional as F
+    from long_context_biomedical_imaging_b200 import ops
+
+    B, cin, dims, patch, hidden = shape
+    torch.manual_seed(5)
+    x = torch.randn(B, cin, *dims, device="cuda", requires_grad=True)
+    w = (torch.randn(hidden, cin, *patch, device="cuda") * 0.05).requires_grad_(True)
+    b = torch.randn(hidden, device="cuda", requires_grad=True)
+    grid = [s // p for s, p in zip(dims, patch)]
+    n_tok = grid[0] * grid[1] * grid[2]
+    pos = torch.randn(1, n_tok, hidden, device="cuda", requires_grad=True)
+    y = ops.patch_embed(x, w, b, pos, grid, torch.float32)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv3d(x.double(), w.double(), b.double(), stride=patch).flatten(2).transpose(1, 2) + pos.double()
+        dout = torch.randn_like(y)
+        gx, gw, gb, gp = torch.autograd.grad(ref, (x, w, b, pos), dout.double())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert max_rel(y.detach().cpu(), ref.detach().float().cpu()) < FP32_TOL
+    y.backward(dout)
+    assert max_rel(w.grad.cpu(), gw.float().cpu()) < FP32_TOL
+    assert max_rel(b.grad.cpu(), gb.float().cpu()) < FP32_TOL
+    assert max_rel(pos.grad.cpu(), gp.float().cpu()) < FP32_TOL
+    assert max_rel(x.grad.cpu(), gx.float().cpu()) < FP32_TOL
+
+
 def _vit_cfg(hidden, mlp, layers, heads, patch, t, h, w, task="seg"):
     return types.SimpleNamespace(ViT=types.SimpleNamespace(size="custom", hidden_size=hidden, mlp_dim=mlp, num_layers=layers,
                                                            num_heads=heads, patch_size=list(patch), use_hyena=False,

@@ -14,7 +14,7 @@ TRACE_LIB = os.path.join(CSRC, "liblcbi_b200_trace.so")
 
 def build():
     srcs = [os.path.join(CSRC, f) for f in ("capi.cu", "dense_attn_fwd.cu", "dense_attn_bwd.cu", "window_attn.cu", "window_attn_small.cu",
-                                            "patch_embed.cu", "attn_merge.cu")]
+                                            "patch_embed.cu", "patch_embed_mma.cu", "attn_merge.cu")]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-lineinfo",
            "-DLCBI_TRACE", "-Xcompiler", "-fPIC", "-shared", "-o", TRACE_LIB] + srcs + ["-lcudart"]
     subprocess.run(cmd, check=True)
