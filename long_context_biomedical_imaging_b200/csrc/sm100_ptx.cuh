@@ -74,7 +74,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
+#if defined(LCBI_MBAR_TEST_WAIT)
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#endif
       "selp.b32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
