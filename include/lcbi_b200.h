@@ -119,6 +119,19 @@ int lcbi_win_attn_bwd(int ndim, const int* grid, const int* window, const int* s
                       const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad, float* dtable,
                       void* stream);
 
+/* Window-sharded variants (the windows of one block are independent, so the flattened (batch, window) list
+ * can be split across GPUs): only windows [win_begin, win_begin + win_count) are processed (win_count < 0: all).
+ * Forward writes `out` / `lse2` rows of the tokens inside those windows only; backward writes the matching `dqkv` rows
+ * and ADDS this range's contribution to dbias_pad / dtable. Every token belongs to exactly one window, so the
+ * per-range results of a partition are disjoint in out / dqkv and sum to the full-block result elsewhere. */
+int lcbi_win_attn_fwd_range(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                            float scale, const void* qkv, const float* qkv_bias, const float* table, void* out,
+                            float* lse2, int win_begin, int win_count, void* stream);
+int lcbi_win_attn_bwd_range(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                            float scale, const void* qkv, const float* qkv_bias, const float* table, const void* o,
+                            const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad,
+                            float* dtable, int win_begin, int win_count, void* stream);
+
 /* Index maps as tensors, for bit-exactness checks against window_partition(roll(pad(.))) (:135-165,:459-468),
  * compute_mask (:591-628) and relative_position_index (:256-308):
  *   gather (nW*n) int32: source token of each window slot, -1 for pad tokens; region (nW*n) int32: shift-mask

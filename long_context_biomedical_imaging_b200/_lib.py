@@ -38,6 +38,12 @@ SIGNATURES = {
                                          ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lcbi_win_attn_bwd": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_float] + [c_vp] * 11),
+    "lcbi_win_attn_fwd_range": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
+                                               ctypes.c_int, c_vp]),
+    "lcbi_win_attn_bwd_range": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_float] + [c_vp] * 10 +
+                                              [ctypes.c_int, ctypes.c_int, c_vp]),
     "lcbi_window_maps": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_i32p, c_i32p, c_vp]),
 }
 

@@ -140,11 +140,19 @@ static int win_status(int rc, const char* who) {
 int lcbi_win_attn_fwd(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
                       float scale, const void* qkv, const float* qkv_bias, const float* table, void* out, float* lse2,
                       void* stream) {
+  return lcbi_win_attn_fwd_range(ndim, grid, window, shift, B, H, head_dim, scale, qkv, qkv_bias, table, out, lse2, 0, -1,
+                                 stream);
+}
+
+int lcbi_win_attn_fwd_range(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                            float scale, const void* qkv, const float* qkv_bias, const float* table, void* out,
+                            float* lse2, int win_begin, int win_count, void* stream) {
   if (!grid || !window || !shift || !qkv || !table || !out || !lse2)
     return fail(LCBI_ERR_BAD_ARG, "lcbi_win_attn_fwd: null pointer argument");
+  if (win_count == 0) return LCBI_OK;
   WinAttnArgs a{};
   a.ndim = ndim; a.grid = grid; a.window = window; a.shift = shift;
-  a.B = B; a.H = H; a.head_dim = head_dim; a.scale = scale;
+  a.B = B; a.H = H; a.head_dim = head_dim; a.scale = scale; a.win_begin = win_begin; a.win_count = win_count;
   a.qkv = qkv; a.qkv_bias = qkv_bias; a.table = table; a.out = out; a.lse2 = lse2;
   return win_status(win_attn_fwd_launch(a, static_cast<cudaStream_t>(stream)), "lcbi_win_attn_fwd");
 }
@@ -153,11 +161,20 @@ int lcbi_win_attn_bwd(int ndim, const int* grid, const int* window, const int* s
                       float scale, const void* qkv, const float* qkv_bias, const float* table, const void* o,
                       const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad, float* dtable,
                       void* stream) {
+  return lcbi_win_attn_bwd_range(ndim, grid, window, shift, B, H, head_dim, scale, qkv, qkv_bias, table, o, lse2, d_out,
+                                 dsum, dqkv, dbias_pad, dtable, 0, -1, stream);
+}
+
+int lcbi_win_attn_bwd_range(int ndim, const int* grid, const int* window, const int* shift, int B, int H, int head_dim,
+                            float scale, const void* qkv, const float* qkv_bias, const float* table, const void* o,
+                            const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad,
+                            float* dtable, int win_begin, int win_count, void* stream) {
   if (!grid || !window || !shift || !qkv || !table || !o || !lse2 || !d_out || !dsum || !dqkv)
     return fail(LCBI_ERR_BAD_ARG, "lcbi_win_attn_bwd: null pointer argument");
+  if (win_count == 0) return LCBI_OK;
   WinAttnArgs a{};
   a.ndim = ndim; a.grid = grid; a.window = window; a.shift = shift;
-  a.B = B; a.H = H; a.head_dim = head_dim; a.scale = scale;
+  a.B = B; a.H = H; a.head_dim = head_dim; a.scale = scale; a.win_begin = win_begin; a.win_count = win_count;
   a.qkv = qkv; a.qkv_bias = qkv_bias; a.table = table; a.lse2 = const_cast<float*>(lse2);
   a.d_out = d_out; a.dsum = dsum; a.dqkv = dqkv; a.dbias_pad = dbias_pad; a.dtable = dtable;
   return win_status(win_attn_bwd_launch(a, o, static_cast<cudaStream_t>(stream)), "lcbi_win_attn_bwd");

@@ -62,6 +62,7 @@ struct WinAttnArgs {
   const int* window;              // constructor window size
   const int* shift;               // constructor shift size (all zeros for W-MSA blocks)
   int B, H, head_dim;
+  int win_begin, win_count;       // range of the flattened (batch, window) list; count < 0: all windows
   float scale;
   const void* qkv;                // bf16 (B, T, 3, H, d)
   const float* qkv_bias;          // fp32 (3*H*d) or null

@@ -102,7 +102,7 @@ win_attn_fwd_kernel(const WinParams p) {
   meta.col_term = meta.row_term + n_pad;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wg = blockIdx.x, h = blockIdx.y;
+  const int wg = p.win_begin + blockIdx.x, h = blockIdx.y;
   const int b = wg / g.nW, w = wg % g.nW;
 
   fill_meta(g, w, n_pad, meta, tid, 128);
@@ -307,7 +307,7 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
   meta.col_term = meta.row_term + n_pad;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wg = blockIdx.x, h = blockIdx.y;
+  const int wg = p.win_begin + blockIdx.x, h = blockIdx.y;
   const int b = wg / g.nW, w = wg % g.nW;
 
   fill_meta(g, w, n_pad, meta, tid, 128);
@@ -502,9 +502,9 @@ win_attn_bwd_dq_kernel(const WinParams p) {
   const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
   const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
   const uint32_t do_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDO));
-  const int total_windows = p.B * g.nW;
+  const int total_windows = p.win_count;
 
-  for (int wg = split; wg < total_windows; wg += p.win_splits) {
+  for (int wg = p.win_begin + split; wg < p.win_begin + total_windows; wg += p.win_splits) {
     const int b = wg / g.nW, w = wg % g.nW;
     __syncthreads();                              // previous window fully consumed
     fill_meta(g, w, n_pad, meta, tid, nthreads);
@@ -694,6 +694,10 @@ int fill_params(WinParams& p, const WinAttnArgs& a) {
   p.dbias_pad = a.dbias_pad;
   p.dtable = a.dtable;
   p.win_splits = 1;
+  const int all_windows = a.B * p.g.nW;
+  p.win_begin = a.win_count < 0 ? 0 : a.win_begin;
+  p.win_count = a.win_count < 0 ? all_windows : a.win_count;
+  if (p.win_begin < 0 || p.win_count < 0 || p.win_begin + p.win_count > all_windows) return LCBI_ERR_BAD_ARG;
   return LCBI_OK;
 }
 
@@ -708,7 +712,7 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
   static const bool use_small = std::getenv("LCBI_WIN_SMALL") != nullptr;
   if (use_small && p.g.n <= 64) return win_attn_fwd_small_launch(p, a.head_dim, stream);
   const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
-  dim3 grid(p.B * p.g.nW, p.H);
+  dim3 grid(p.win_count, p.H);
   if (a.head_dim == 16) {
     if ((rc = set_smem(win_attn_fwd_kernel<16, true>, smem))) return rc;
     win_attn_fwd_kernel<16, true><<<grid, 128, smem, stream>>>(p);
@@ -744,7 +748,7 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
   // 2. dK, dV (+ pad-token bias gradient)
   {
     const size_t smem = dkdv_smem_bytes(p.g, D);
-    dim3 grid(p.B * p.g.nW, p.H);
+    dim3 grid(p.win_count, p.H);
     if (D == 16) {
       if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16, true>, smem))) return rc;
       win_attn_bwd_dkdv_kernel<16, true><<<grid, 128, smem, stream>>>(p);
@@ -765,7 +769,7 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
     const int slab_rows = 16 * qt;
     const size_t smem = dq_smem_bytes(p.g, D, slab_rows);
     const int n_slabs = (p.g.n + slab_rows - 1) / slab_rows;
-    const int total_windows = p.B * p.g.nW;
+    const int total_windows = p.win_count;
     int splits = (6 * 148 + n_slabs * p.H - 1) / (n_slabs * p.H);   // aim at ~6 CTAs' worth of work per SM
     if (splits > total_windows) splits = total_windows;
     if (splits < 1) splits = 1;

@@ -73,10 +73,10 @@ win_attn_fwd_small_kernel(const WinParams p) {
   const int gq = lane >> 2, qq = lane & 3;
   const float mask_log2 = -100.0f * kLog2e;
   const int n_qt = (n + 15) / 16;
-  const int units = p.B * g.nW;
+  const int units = p.win_count;
 
   for (int u = blockIdx.x * kWarps + warp; u < units; u += gridDim.x * kWarps) {
-    const int b = u / g.nW, w = u % g.nW;
+    const int b = (p.win_begin + u) / g.nW, w = (p.win_begin + u) % g.nW;
     // ---- window metadata: two slots per lane
     int first_reg = 0;
     bool differs = false;
@@ -236,7 +236,7 @@ int launch_small(const WinParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  const int units = p.B * p.g.nW;
+  const int units = p.win_count;
   const int ctas_per_sm = (227 * 1024) / (L::kTotal + 1024);
   int grid_x = (148 * (ctas_per_sm > 0 ? ctas_per_sm : 1) + p.H - 1) / p.H;
   const int max_x = (units + kWarps - 1) / kWarps;
@@ -317,7 +317,7 @@ win_attn_bwd_small_kernel(const WinParams p) {
   const int gq = lane >> 2, qq = lane & 3;
   const float mask_log2 = -100.0f * kLog2e;
   const float scale = p.scale_log2 / kLog2e;
-  const int units = p.B * g.nW;
+  const int units = p.win_count;
   const int row0 = warp * 16;                       // this warp's query tile (phase 1) and key tile (phase 2)
   const bool tile_live = row0 < n;
 
@@ -329,7 +329,7 @@ win_attn_bwd_small_kernel(const WinParams p) {
   for (int i = 0; i < D / 8; ++i) pad_dk[i][0] = pad_dk[i][1] = pad_dv[i][0] = pad_dv[i][1] = 0.f;
 
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int b = u / g.nW, w = u % g.nW;
+    const int b = (p.win_begin + u) / g.nW, w = (p.win_begin + u) % g.nW;
     __syncthreads();                                // previous window fully consumed (and tab / terms written)
     if (tid < 64) {
       int tok = -2, reg = -1;
@@ -555,7 +555,7 @@ int launch_small_bwd(const WinParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_bytes = smem;
   }
-  const int units = p.B * p.g.nW;
+  const int units = p.win_count;
   int ctas_per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   if (ctas_per_sm > 3) ctas_per_sm = 3;             // register-limited (launch bounds)
   if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -106,6 +106,7 @@ struct WinParams {
   float* dbias_pad;             // (3*C) fp32, += gradient reaching qkv.bias through the pad tokens
   float* dtable;                // (tab_rows, H) fp32, +=
   int win_splits;               // dq kernel: number of window subsets
+  int win_begin, win_count;     // range of the flattened (batch, window) list this launch processes
 };
 
 template <int D>

@@ -210,20 +210,25 @@ class _WindowAttention(torch.autograd.Function):
     qkv_bias (3*H*d) supplies the q/k/v rows of pad tokens; table is relative_position_bias_table."""
 
     @staticmethod
-    def forward(ctx, qkv, qkv_bias, table, grid, window, shift, scale):
+    def forward(ctx, qkv, qkv_bias, table, grid, window, shift, scale, win_range=None):
         _require_cuda(qkv, table)
         B, T, _, H, d = qkv.shape
         qkv = qkv.contiguous()
         bias_f = qkv_bias.detach().float().contiguous() if qkv_bias is not None else None
         table_f = table.detach().float().contiguous()
-        out = torch.empty((B, T, H * d), dtype=torch.bfloat16, device=qkv.device)
-        lse2 = torch.empty((B, T, H), dtype=torch.float32, device=qkv.device)
+        # a window range leaves the rows of all other windows' tokens untouched: they must read as zero
+        alloc = torch.empty if win_range is None else torch.zeros
+        out = alloc((B, T, H * d), dtype=torch.bfloat16, device=qkv.device)
+        lse2 = alloc((B, T, H), dtype=torch.float32, device=qkv.device)
+        begin, count = (0, -1) if win_range is None else (int(win_range[0]), int(win_range[1]))
         lib = _lib.load()
         g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
-        rc = lib.lcbi_win_attn_fwd(len(grid), g, w, s, B, H, d, float(scale), _p(qkv),
-                                   _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2), _stream())
-        _lib.check(rc, "lcbi_win_attn_fwd")
+        rc = lib.lcbi_win_attn_fwd_range(len(grid), g, w, s, B, H, d, float(scale), _p(qkv),
+                                         _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2),
+                                         begin, count, _stream())
+        _lib.check(rc, "lcbi_win_attn_fwd_range")
         ctx.save_for_backward(qkv, bias_f, table_f, out, lse2)
+        ctx.win_range = (begin, count)
         ctx.geom = (tuple(grid), tuple(window), tuple(shift), float(scale))
         ctx.meta = (None if qkv_bias is None else qkv_bias.dtype, table.dtype)
         return out
@@ -235,22 +240,29 @@ class _WindowAttention(torch.autograd.Function):
         B, T, _, H, d = qkv.shape
         d_out = d_out.to(torch.bfloat16).contiguous()
         dev = qkv.device
-        dqkv = torch.empty_like(qkv)
+        begin, count = ctx.win_range
+        dqkv = torch.empty_like(qkv) if count < 0 else torch.zeros_like(qkv)
         dsum = torch.empty((B, T, H), dtype=torch.float32, device=dev)
         dbias = torch.zeros((3 * H * d,), dtype=torch.float32, device=dev) if bias_f is not None else None
         dtable = torch.zeros_like(table_f)
         lib = _lib.load()
         g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
-        rc = lib.lcbi_win_attn_bwd(len(grid), g, w, s, B, H, d, scale, _p(qkv), _p(bias_f) if bias_f is not None else None,
-                                   _p(table_f), _p(out), _p(lse2), _p(d_out), _p(dsum), _p(dqkv),
-                                   _p(dbias) if dbias is not None else None, _p(dtable), _stream())
-        _lib.check(rc, "lcbi_win_attn_bwd")
+        rc = lib.lcbi_win_attn_bwd_range(len(grid), g, w, s, B, H, d, scale, _p(qkv),
+                                         _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2),
+                                         _p(d_out), _p(dsum), _p(dqkv), _p(dbias) if dbias is not None else None,
+                                         _p(dtable), begin, count, _stream())
+        _lib.check(rc, "lcbi_win_attn_bwd_range")
         bias_dtype, table_dtype = ctx.meta
-        return (dqkv, dbias.to(bias_dtype) if dbias is not None else None, dtable.to(table_dtype), None, None, None, None)
+        return (dqkv, dbias.to(bias_dtype) if dbias is not None else None, dtable.to(table_dtype), None, None, None, None,
+                None)
 
 
-def window_attention(qkv, qkv_bias, table, grid, window, shift, num_heads, scale=None):
+def window_attention(qkv, qkv_bias, table, grid, window, shift, num_heads, scale=None, win_range=None):
     """Fused Swin (shifted-)window attention on the token grid.
+
+    win_range = (begin, count) restricts the call to a range of the flattened (batch, window) list (window-sharded
+    execution, `window_parallel.py`): rows of tokens outside those windows come back as zeros, and the parameter
+    gradients are this range's contribution only.
 
     qkv: (B, *grid, 3*C) output of the qkv Linear applied to the un-padded, un-shifted tokens (feature index
     s*C + h*d + j, reference backbone_swin.py:339); qkv_bias: the Linear's bias (q/k/v of pad tokens) or None;
@@ -270,7 +282,7 @@ def window_attention(qkv, qkv_bias, table, grid, window, shift, num_heads, scale
         scale = d ** -0.5
     x = qkv if qkv.dtype == torch.bfloat16 else qkv.to(torch.bfloat16)
     out = _WindowAttention.apply(x.reshape(B, T, 3, num_heads, d), qkv_bias, table, grid,
-                                 tuple(int(v) for v in window), tuple(int(v) for v in shift), float(scale))
+                                 tuple(int(v) for v in window), tuple(int(v) for v in shift), float(scale), win_range)
     out = out.view(B, *grid, C)
     return out if out.dtype == qkv.dtype else out.to(qkv.dtype)
 

@@ -118,6 +118,45 @@ def swin_part1(x, window_ctor, shift_ctor, w_qkv, b_qkv, table, w_proj, b_proj, 
     return out.reshape(x.shape)
 
 
+def window_attention_core(qkv, qkv_bias, table, grid, window_ctor, shift_ctor, num_heads, scale=None, win_range=None):
+    """The part of forward_part1 between the qkv Linear and the proj Linear (backbone_swin.py:339-357 inside
+    :441-485), on the un-padded token grid: qkv (B, *grid, 3C) with feature index s*C + h*d + j (:339). Pad tokens
+    enter the reference as zeros BEFORE the Linear (:441-455), so their q/k/v rows are the Linear's bias.
+    win_range = (begin, count) keeps only the windows [begin, begin+count) of the flattened (batch, window) list and
+    returns zeros for the tokens of all other windows (window-sharded execution)."""
+    B, C = qkv.shape[0], qkv.shape[-1] // 3
+    d = C // num_heads
+    scale = d ** -0.5 if scale is None else scale
+    grid = tuple(int(g) for g in grid)
+    win, sh = wm.resolve_window(grid, window_ctor, shift_ctor)
+    n = int(np.prod(win))
+    gmap = torch.from_numpy(wm.gather_map(grid, window_ctor, shift_ctor)).to(qkv.device)  # (nW, n)
+    nW = gmap.shape[0]
+    flat = qkv.reshape(B, -1, 3 * C)
+    valid = gmap >= 0
+    idx = gmap.clamp(min=0)
+    rows = flat[:, idx.reshape(-1)].reshape(B, nW, n, 3 * C)
+    pad_row = qkv_bias if qkv_bias is not None else torch.zeros(3 * C, dtype=qkv.dtype, device=qkv.device)
+    rows = torch.where(valid[None, :, :, None], rows, pad_row.to(rows.dtype).expand_as(rows))
+    t = rows.reshape(B * nW, n, 3, num_heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0] * scale, t[1], t[2]
+    s = q @ k.transpose(-2, -1)
+    index_nn = torch.from_numpy(wm.rel_pos_index_used(window_ctor, n)).to(qkv.device)
+    s = s + table[index_nn.reshape(-1)].reshape(n, n, num_heads).permute(2, 0, 1).unsqueeze(0)
+    if any(x > 0 for x in sh):
+        mask = torch.from_numpy(wm.shift_mask(grid, window_ctor, shift_ctor)).to(device=qkv.device, dtype=s.dtype)
+        s = (s.view(B, nW, num_heads, n, n) + mask[None, :, None]).view(B * nW, num_heads, n, n)
+    o = (s.softmax(dim=-1) @ v).transpose(1, 2).reshape(B, nW, n, C)
+    if win_range is not None:
+        unit = torch.arange(B * nW, device=qkv.device).reshape(B, nW)
+        keep = (unit >= win_range[0]) & (unit < win_range[0] + win_range[1])
+        o = o * keep[:, :, None, None].to(o.dtype)
+    out = torch.zeros(B, flat.shape[1], C, dtype=o.dtype, device=qkv.device)
+    sel = valid.reshape(-1)
+    out[:, idx.reshape(-1)[sel]] = o.reshape(B, nW * n, C)[:, sel]
+    return out.reshape(B, *grid, C)
+
+
 # ------------------------------------------------------------------------------------------------
 # patch embedding (MONAI 1.3.0 semantics)
 # ------------------------------------------------------------------------------------------------

@@ -191,3 +191,45 @@ def test_swin_inference_mode_and_rejections():
     with pytest.raises(ValueError):   # head_dim 8 unsupported
         ops.window_attention(torch.randn(1, 8, 8, 3 * 16, device="cuda"), None, torch.zeros(169, 2, device="cuda"),
                              (8, 8), (7, 7), (0, 0), 2)
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=2, grid=(14, 21), window=(7, 7), shift=(3, 3), heads=3, d=32),          # fused small-window kernels
+    dict(B=1, grid=(9, 10, 8), window=(7, 7, 7), shift=(3, 3, 3), heads=2, d=16),  # 343-token windows: dkdv + dq kernels
+])
+def test_window_ranges_partition_the_block(case):
+    """lcbi_win_attn_{fwd,bwd}_range: the results of a partition of the (batch, window) list are disjoint in out / dqkv
+    and add up to the full-block result (what window_parallel.py relies on); each range also matches the oracle."""
+    from long_context_biomedical_imaging_b200 import ops
+    from long_context_biomedical_imaging_b200.window_parallel import count_windows, shard_range
+    from oracle import attention_oracle as ao
+
+    torch.manual_seed(7)
+    B, grid, heads, d = case["B"], case["grid"], case["heads"], case["d"]
+    C = heads * d
+    qkv = (torch.randn(B, *grid, 3 * C, device="cuda") * 0.7).to(torch.bfloat16).requires_grad_(True)
+    bias = torch.randn(3 * C, device="cuda").requires_grad_(True)
+    n_tab = 1
+    for w in case["window"]:
+        n_tab *= 2 * w - 1
+    table = (torch.randn(n_tab, heads, device="cuda") * 0.5).requires_grad_(True)
+    d_out = torch.randn(B, *grid, C, device="cuda").to(torch.bfloat16)
+
+    full = ops.window_attention(qkv, bias, table, grid, case["window"], case["shift"], heads)
+    g_full = torch.autograd.grad(full, (qkv, bias, table), d_out)
+    total = B * count_windows(grid, case["window"])
+    out_sum, g_sum = torch.zeros_like(full, dtype=torch.float32), [torch.zeros_like(t, dtype=torch.float32) for t in g_full]
+    for r in range(3):
+        rng = shard_range(total, 3, r)
+        part = ops.window_attention(qkv, bias, table, grid, case["window"], case["shift"], heads, win_range=rng)
+        want = ao.window_attention_core(qkv.detach().float().cpu(), bias.detach().cpu(), table.detach().cpu(), grid,
+                                        case["window"], case["shift"], heads, win_range=rng)
+        assert max_rel(part.detach().float().cpu(), want) < BF16_TOL
+        assert int(((part != 0) & (out_sum != 0)).sum()) == 0          # disjoint token rows
+        out_sum += part.detach().float()
+        for acc, g in zip(g_sum, torch.autograd.grad(part, (qkv, bias, table), d_out)):
+            acc += g.float()
+    assert torch.equal(out_sum.to(torch.bfloat16), full.detach())       # the same kernel wrote every row: bit-identical
+    assert torch.equal(g_sum[0].to(torch.bfloat16), g_full[0])           # dqkv rows are disjoint too
+    assert max_rel(g_sum[1].cpu(), g_full[1].float().cpu()) < 1e-3      # fp32 atomics: order differs
+    assert max_rel(g_sum[2].cpu(), g_full[2].float().cpu()) < 1e-3
