@@ -222,6 +222,93 @@ def run_cfg5(args, dist, rank, world, local_rank):
     dist.destroy_process_group()
 
 
+def run_swin(args, dist, rank, world, local_rank):
+    """configs[1] / configs[3]: the window attention of one stage-1 Swin block (SW-MSA, shift = window // 2), fwd+bwd.
+    cfg2 (Swin-T 2D, 512^2, patch 4 -> 128^2 tokens x 96 channels, 3 heads x 32, window 7, batch 16 per GPU) shards
+    the batch: no data-path collective, weak scaling. cfg4 (Swin 3D 'unetr', 128^3, patch 2 -> 64^3 tokens x 48
+    channels, 3 heads x 16, window 7^3 = 343 tokens, batch 1) shards the 1000 windows over the ranks
+    (window_parallel.py: one all-reduce forward, gradient all-reduces backward): strong scaling."""
+    from long_context_biomedical_imaging_b200 import ops, window_parallel
+
+    if dist is None and args.workload == "cfg4":
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29534")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    if args.workload == "cfg2":
+        B, grid, C, H, window, what = 16, (128, 128), 96, 3, (7, 7), "cfg2: Swin-T 2D 512^2 patch 4, stage-1 SW-MSA block attention, window 7, batch 16 per GPU"
+        torch.manual_seed(rank)
+    else:
+        B, grid, C, H, window, what = 1, (64, 64, 64), 48, 3, (7, 7, 7), "cfg4: Swin 3D 'unetr' 128^3 patch 2, stage-1 SW-MSA block attention, window 7^3, batch 1"
+        torch.manual_seed(0)                  # replicated tokens
+    shift = tuple(w // 2 for w in window)
+    n_tab = 1
+    for w in window:
+        n_tab *= 2 * w - 1
+    qkv = torch.randn(B, *grid, 3 * C, device=dev).to(torch.bfloat16).requires_grad_(True)
+    bias = torch.randn(3 * C, device=dev).requires_grad_(True)
+    table = (torch.randn(n_tab, H, device=dev) * 0.5).requires_grad_(True)
+    d_out = torch.randn(B, *grid, C, device=dev).to(torch.bfloat16)
+    steps = args.steps if args.steps is not None else 50
+    warmup = max(3, args.warmup if args.warmup is not None else 5)
+
+    def step():
+        if args.workload == "cfg4":
+            out = window_parallel.window_attention_sharded(qkv, bias, table, grid, window, shift, H)
+        else:
+            out = ops.window_attention(qkv, bias, table, grid, window, shift, H)
+        out.backward(d_out)
+        qkv.grad = bias.grad = table.grad = None
+
+    for _ in range(warmup):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        peaks = measured_peaks()
+        n_tok = B
+        for g in grid:
+            n_tok *= g
+        weak = args.workload == "cfg2"
+        tokens_job = n_tok * (world if weak else 1)
+        ms_step = ms / steps
+        alg_bytes = 24.0 * C * n_tok                   # per GPU-sized problem: q,k,v,o read/written fwd + bwd (SURVEY 8d)
+        gbs = alg_bytes * (1 if weak else 1.0 / world) / (ms_step * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": tokens_job / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if weak else "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": what,
+                       "parallelism": (f"batch-sharded x{world} (no data-path collective)" if weak else
+                                       f"windows sharded x{world} (all-reduce of outputs and of replicated-input gradients)"),
+                       "tokens_per_step": tokens_job},
+            "roofline": {"bound": "hbm", "kernel": "window attention fwd + bwd launch group", "achieved": gbs,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                         "algorithmic_bytes_per_step_per_gpu": alg_bytes * (1 if weak else 1.0 / world),
+                         "note": "includes the autograd wrapper and, for cfg4, the collectives"},
+            "gpu_launches": steps * 4}), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of dense_attn_bwd_kernel at 16 volumes (276.9 MB + 127.1 MB), per volume
 BWD_DRAM_BYTES_PER_VOLUME = (276_902_400 + 127_062_784) // 16
 
@@ -234,9 +321,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG3["B"], help="volumes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5"],
-                    help="cfg3 (default, headline) or cfg5: ViT-B 2D 1024^2 patch 2 = 262,144 tokens, ring K/V "
-                         "sequence-parallel over the ranks (strong scaling)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg2", "cfg4"],
+                    help="cfg3 (default, headline); cfg5: ViT-B 2D 1024^2 patch 2 = 262,144 tokens, ring K/V "
+                         "sequence-parallel over the ranks (strong scaling); cfg2 / cfg4: stage-1 Swin window attention, "
+                         "batch-sharded (2-D) / window-sharded (3-D)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -265,6 +353,9 @@ def main():
 
     if args.workload == "cfg5":
         run_cfg5(args, dist, rank, world, local_rank)
+        return
+    if args.workload in ("cfg2", "cfg4"):
+        run_swin(args, dist, rank, world, local_rank)
         return
 
     B, N, H, d, C = args.batch, CFG3["N"], CFG3["H"], CFG3["d"], CFG3["C"]
