@@ -17,7 +17,13 @@
 #include <cstdlib>
 
 #include "lcbi_kernels.h"
+#include <type_traits>
+
 #include "window_common.cuh"
+
+#ifndef LCBI_WIN_NT
+#define LCBI_WIN_NT 256   /* threads per CTA of the large-window forward / dK-dV kernels (measured: see DESIGN.md) */
+#endif
 
 namespace lcbi {
 
@@ -48,6 +54,15 @@ __device__ __forceinline__ void fill_meta(const WinGeom& g, int w, int n_pad, Wi
     m.row_term[s] = rt;
     m.col_term[s] = ct;
   }
+}
+
+// true when the window straddles a shift-mask region boundary (only then do the -100 terms exist); warp-uniform.
+// Most windows (all of them in an un-shifted block) are region-uniform and take the cheaper logit path.
+__device__ __forceinline__ bool window_has_mask(const WinGeom& g, const WinMeta& m, int tid, int nthreads) {
+  bool differs = false;
+  const int r0 = m.reg[0];
+  for (int s = tid; s < g.n; s += nthreads) differs |= m.reg[s] != r0;
+  return __syncthreads_or(differs) != 0;
 }
 
 // loads rows [row_begin, row_end) of one of q/k/v (or dO when sel == 3) for (batch b, head h) into a smem tile
@@ -84,8 +99,8 @@ __device__ __forceinline__ void load_rows(uint8_t* tile, const WinParams& p, con
 // kHighOcc: cap registers for 6 (D=32: a few spills) CTAs per SM. Measured on B200: a win when the window is one
 // key chunk (n <= 64: the kernel is latency-bound, 235 -> 192 us at cfg2 stage 1) and for d = 16; a loss for
 // d = 32 with 343-token windows, where the spills land in the six-iteration key loop.
-template <int D, bool kHighOcc>
-__global__ void __launch_bounds__(128, kHighOcc ? 6 : 1)
+template <int D, bool kHighOcc, int NT = 128>
+__global__ void __launch_bounds__(NT, kHighOcc ? (NT == 128 ? 6 : (NT == 256 ? 3 : 2)) : 1)
 win_attn_fwd_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const WinGeom& g = p.g;
@@ -103,14 +118,16 @@ win_attn_fwd_kernel(const WinParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wg = p.win_begin + blockIdx.x, h = blockIdx.y;
-  const int b = wg / g.nW, w = wg % g.nW;
+  int b, w;
+  fdivmod(wg, g.d_nW, b, w);
 
-  fill_meta(g, w, n_pad, meta, tid, 128);
-  for (int t = tid; t < g.tab_rows; t += 128) tab[t] = p.table[t * p.H + h] * kLog2e;
+  fill_meta(g, w, n_pad, meta, tid, NT);
+  for (int t = tid; t < g.tab_rows; t += NT) tab[t] = p.table[t * p.H + h] * kLog2e;
   __syncthreads();
-  load_rows<D>(sQ, p, meta.tok, b, h, 0, 0, n_pad, tid, 128);
-  load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, 128);
-  load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, 128);
+  const bool has_mask = window_has_mask(g, meta, tid, NT);
+  load_rows<D>(sQ, p, meta.tok, b, h, 0, 0, n_pad, tid, NT);
+  load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, NT);
+  load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, NT);
   __syncthreads();
 
   const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
@@ -120,7 +137,7 @@ win_attn_fwd_kernel(const WinParams p) {
   const float mask_log2 = -100.0f * kLog2e;
   const int n_qt = (n + 15) / 16;
 
-  for (int qt = warp; qt < n_qt; qt += 4) {
+  for (int qt = warp; qt < n_qt; qt += NT / 32) {
     const int row0 = qt * 16;
     uint32_t aq[D / 16][4];
 #pragma unroll
@@ -145,25 +162,35 @@ win_attn_fwd_kernel(const WinParams p) {
           mma_bf16_16816(s[nt], aq[kk], b0, b1);
         }
       }
-      // logits (log2 domain) = s*scale*log2e + bias*log2e + mask*log2e ; columns beyond the window -> -inf
+      // logits (log2 domain) = s*scale*log2e + bias*log2e + mask*log2e ; columns beyond the window -> -inf.
+      // Dead columns carry col_term 0, so the table gather stays in range without a bounds check; only the last key
+      // chunk can hold them, and only windows that straddle a region boundary need the mask term.
       float cmax0 = -INFINITY, cmax1 = -INFINITY;
+      const bool tail = kc + kKeyChunk > n;
+      auto logits = [&](auto masked_c) {
+        constexpr bool kMasked = decltype(masked_c)::value;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = kc + nt * 8 + qq * 2 + e;
-          float v0 = -INFINITY, v1 = -INFINITY;
-          if (j < n) {
-            const int ct = meta.col_term[j], rj = meta.reg[j];
-            v0 = fmaf(s[nt][e], p.scale_log2, tab[rt0 - ct]) + (rg0 != rj ? mask_log2 : 0.f);
-            v1 = fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - ct]) + (rg1 != rj ? mask_log2 : 0.f);
+        for (int nt = 0; nt < 8; ++nt) {
+          const int j = kc + nt * 8 + qq * 2;
+          const int2 ct = *reinterpret_cast<const int2*>(meta.col_term + j);
+          int2 rj = make_int2(0, 0);
+          if (kMasked) rj = *reinterpret_cast<const int2*>(meta.reg + j);
+          float v00 = fmaf(s[nt][0], p.scale_log2, tab[rt0 - ct.x]), v01 = fmaf(s[nt][1], p.scale_log2, tab[rt0 - ct.y]);
+          float v10 = fmaf(s[nt][2], p.scale_log2, tab[rt1 - ct.x]), v11 = fmaf(s[nt][3], p.scale_log2, tab[rt1 - ct.y]);
+          if (kMasked) {
+            v00 += rg0 != rj.x ? mask_log2 : 0.f; v01 += rg0 != rj.y ? mask_log2 : 0.f;
+            v10 += rg1 != rj.x ? mask_log2 : 0.f; v11 += rg1 != rj.y ? mask_log2 : 0.f;
           }
-          s[nt][e] = v0;
-          s[nt][2 + e] = v1;
-          cmax0 = fmaxf(cmax0, v0);
-          cmax1 = fmaxf(cmax1, v1);
+          if (tail) {
+            if (j >= n) v00 = v10 = -INFINITY;
+            if (j + 1 >= n) v01 = v11 = -INFINITY;
+          }
+          s[nt][0] = v00; s[nt][1] = v01; s[nt][2] = v10; s[nt][3] = v11;
+          cmax0 = fmaxf(cmax0, fmaxf(v00, v01));
+          cmax1 = fmaxf(cmax1, fmaxf(v10, v11));
         }
-      }
+      };
+      if (has_mask) logits(std::true_type{}); else logits(std::false_type{});
       cmax0 = fmaxf(cmax0, __shfl_xor_sync(0xffffffffu, cmax0, 1));
       cmax0 = fmaxf(cmax0, __shfl_xor_sync(0xffffffffu, cmax0, 2));
       cmax1 = fmaxf(cmax1, __shfl_xor_sync(0xffffffffu, cmax1, 1));
@@ -286,8 +313,8 @@ __device__ __forceinline__ void load_row_scalars(const WinParams& p, const int* 
 // backward dK/dV: CTA = (window, head), 4 warps, each warp owns 16-row KEY tiles and sweeps the queries
 //   S^T = K Q^T, P^T = exp2(.), dP^T = V dO^T, dS^T = P^T o (dP^T - D[q]); dV += P^T dO; dK += dS^T Q
 // =================================================================================================
-template <int D, bool kHighOcc>
-__global__ void __launch_bounds__(128, kHighOcc ? 5 : 1)
+template <int D, bool kHighOcc, int NT = 128>
+__global__ void __launch_bounds__(NT, kHighOcc ? (NT == 128 ? 5 : (NT == 256 ? 2 : 1)) : 1)
 win_attn_bwd_dkdv_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const WinGeom& g = p.g;
@@ -308,16 +335,24 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wg = p.win_begin + blockIdx.x, h = blockIdx.y;
-  const int b = wg / g.nW, w = wg % g.nW;
+  int b, w;
+  fdivmod(wg, g.d_nW, b, w);
 
-  fill_meta(g, w, n_pad, meta, tid, 128);
-  for (int t = tid; t < g.tab_rows; t += 128) tab[t] = p.table[t * p.H + h] * kLog2e;
+  fill_meta(g, w, n_pad, meta, tid, NT);
+  for (int t = tid; t < g.tab_rows; t += NT) tab[t] = p.table[t * p.H + h] * kLog2e;
   __syncthreads();
-  load_rows<D>(sQ, p, meta.tok, b, h, 0, 0, n_pad, tid, 128);
-  load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, 128);
-  load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, 128);
-  load_rows<D>(sDO, p, meta.tok, b, h, 3, 0, n_pad, tid, 128);
-  load_row_scalars(p, meta.tok, b, h, 0, n_pad, s_lse, s_dsum, tid, 128);
+  load_rows<D>(sQ, p, meta.tok, b, h, 0, 0, n_pad, tid, NT);
+  load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, NT);
+  load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, NT);
+  load_rows<D>(sDO, p, meta.tok, b, h, 3, 0, n_pad, tid, NT);
+  load_row_scalars(p, meta.tok, b, h, 0, n_pad, s_lse, s_dsum, tid, NT);
+  __syncthreads();
+  const bool has_mask = window_has_mask(g, meta, tid, NT);
+  // per-query column data in one 16-byte record {lse2, dsum, row_term, region}: one LDS.128 per column below
+  // (own array at the end of the dynamic smem, see dkdv_smem_bytes)
+  float4* qcol = reinterpret_cast<float4*>(meta.col_term + n_pad);
+  for (int i = tid; i < n_pad; i += NT)
+    qcol[i] = make_float4(s_lse[i], s_dsum[i], __int_as_float(meta.row_term[i]), __int_as_float(meta.reg[i]));
   __syncthreads();
 
   const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
@@ -332,7 +367,7 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) pad_dk[i][0] = pad_dk[i][1] = pad_dv[i][0] = pad_dv[i][1] = 0.f;
 
-  for (int kt = warp; kt < n_kt; kt += 4) {
+  for (int kt = warp; kt < n_kt; kt += NT / 32) {
     const int key0 = kt * 16;
     uint32_t ak[D / 16][4], av[D / 16][4];
 #pragma unroll
@@ -365,22 +400,30 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
           mma_bf16_16816(dp[nt], av[kk], b0, b1);
         }
       }
+      auto probs = [&](auto masked_c) {
+        constexpr bool kMasked = decltype(masked_c)::value;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = qc + nt * 8 + qq * 2 + e;     // query index (column of the transposed tile)
-          const float lse = s_lse[i], dsm = s_dsum[i];
-          const int rt = meta.row_term[i], ri = meta.reg[i];
-          float p0 = 0.f, p1 = 0.f;
-          if (kv0) p0 = ex2f(fmaf(st[nt][e], p.scale_log2, tab[rt - ct0]) + (ri != rg0 ? mask_log2 : 0.f) - lse);
-          if (kv1) p1 = ex2f(fmaf(st[nt][2 + e], p.scale_log2, tab[rt - ct1]) + (ri != rg1 ? mask_log2 : 0.f) - lse);
-          st[nt][e] = p0;
-          st[nt][2 + e] = p1;
-          dp[nt][e] = p0 * (dp[nt][e] - dsm);
-          dp[nt][2 + e] = p1 * (dp[nt][2 + e] - dsm);
+          for (int e = 0; e < 2; ++e) {
+            const float4 qc4 = qcol[qc + nt * 8 + qq * 2 + e];    // query (column of the transposed tile): lse2, dsum, rt, region
+            const int rt = __float_as_int(qc4.z);
+            float l0 = fmaf(st[nt][e], p.scale_log2, tab[rt - ct0]) - qc4.x;
+            float l1 = fmaf(st[nt][2 + e], p.scale_log2, tab[rt - ct1]) - qc4.x;
+            if (kMasked) {
+              const int ri = __float_as_int(qc4.w);
+              l0 += ri != rg0 ? mask_log2 : 0.f;
+              l1 += ri != rg1 ? mask_log2 : 0.f;
+            }
+            const float p0 = kv0 ? ex2f(l0) : 0.f, p1 = kv1 ? ex2f(l1) : 0.f;
+            st[nt][e] = p0;
+            st[nt][2 + e] = p1;
+            dp[nt][e] = p0 * (dp[nt][e] - qc4.y);
+            dp[nt][2 + e] = p1 * (dp[nt][2 + e] - qc4.y);
+          }
         }
-      }
+      };
+      if (has_mask) probs(std::true_type{}); else probs(std::false_type{});
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {   // 16 queries per MMA k-step
         uint32_t ap[4], ads[4];
@@ -449,7 +492,8 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
 size_t dkdv_smem_bytes(const WinGeom& g, int D) {
   const int n_pad = round_up(g.n, kKeyChunk);
   return static_cast<size_t>(4) * n_pad * (D * 2 + 16) + static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 +
-         static_cast<size_t>(n_pad) * 8 + static_cast<size_t>(n_pad) * 16;
+         static_cast<size_t>(n_pad) * 8 + static_cast<size_t>(n_pad) * 16 +
+         static_cast<size_t>(n_pad) * 16;   // lse/dsum, the four meta arrays, the packed per-query records
 }
 
 // =================================================================================================
@@ -505,10 +549,12 @@ win_attn_bwd_dq_kernel(const WinParams p) {
   const int total_windows = p.win_count;
 
   for (int wg = p.win_begin + split; wg < p.win_begin + total_windows; wg += p.win_splits) {
-    const int b = wg / g.nW, w = wg % g.nW;
+    int b, w;
+  fdivmod(wg, g.d_nW, b, w);
     __syncthreads();                              // previous window fully consumed
     fill_meta(g, w, n_pad, meta, tid, nthreads);
     __syncthreads();
+    const bool has_mask = window_has_mask(g, meta, tid, nthreads);
     load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, nthreads);
     load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, nthreads);
     // slab rows: Q and dO (rows beyond n_pad cannot occur: row_base + 32 <= round_up(n, 32) <= n_pad)
@@ -575,25 +621,35 @@ win_attn_bwd_dq_kernel(const WinParams p) {
           mma_bf16_16816(dp[nt], ado[kk], b0, b1);
         }
       }
+      const bool tail = key0 + 32 > n;           // only then can a key column be a dead slot
+      auto grads = [&](auto masked_c) {
+        constexpr bool kMasked = decltype(masked_c)::value;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < 4; ++nt) {
+          const int j = key0 + nt * 8 + qq * 2;
+          const int2 ct = *reinterpret_cast<const int2*>(meta.col_term + j);
+          int2 rj = make_int2(0, 0);
+          if (kMasked) rj = *reinterpret_cast<const int2*>(meta.reg + j);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = key0 + nt * 8 + qq * 2 + e;
-          float d0 = 0.f, d1 = 0.f;
-          if (j < n) {
-            const int ct = meta.col_term[j], rj = meta.reg[j];
-            const float p0 = ex2f(fmaf(s[nt][e], p.scale_log2, tab[rt0 - ct]) + (rg0 != rj ? mask_log2 : 0.f) - lse0);
-            const float p1 = ex2f(fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - ct]) + (rg1 != rj ? mask_log2 : 0.f) - lse1);
-            d0 = p0 * (dp[nt][e] - ds0);
-            d1 = p1 * (dp[nt][2 + e] - ds1);
+          for (int e = 0; e < 2; ++e) {
+            const int cte = e ? ct.y : ct.x;
+            float l0 = fmaf(s[nt][e], p.scale_log2, tab[rt0 - cte]) - lse0;
+            float l1 = fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - cte]) - lse1;
+            if (kMasked) {
+              const int rje = e ? rj.y : rj.x;
+              l0 += rg0 != rje ? mask_log2 : 0.f;
+              l1 += rg1 != rje ? mask_log2 : 0.f;
+            }
+            float d0 = ex2f(l0) * (dp[nt][e] - ds0), d1 = ex2f(l1) * (dp[nt][2 + e] - ds1);
+            if (tail && j + e >= n) d0 = d1 = 0.f;
+            dp[nt][e] = d0;
+            dp[nt][2 + e] = d1;
+            dbias[sub * 4 + nt][e] += d0;
+            dbias[sub * 4 + nt][2 + e] += d1;
           }
-          dp[nt][e] = d0;
-          dp[nt][2 + e] = d1;
-          dbias[sub * 4 + nt][e] += d0;
-          dbias[sub * 4 + nt][2 + e] += d1;
         }
-      }
+      };
+      if (has_mask) grads(std::true_type{}); else grads(std::false_type{});
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         uint32_t ads[4];
@@ -714,14 +770,19 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
   dim3 grid(p.win_count, p.H);
   if (a.head_dim == 16) {
-    if ((rc = set_smem(win_attn_fwd_kernel<16, true>, smem))) return rc;
-    win_attn_fwd_kernel<16, true><<<grid, 128, smem, stream>>>(p);
+    if (p.g.n > 128) {      // eight warps share the window's tiles: twice the warps per SM for the same smem
+      if ((rc = set_smem(win_attn_fwd_kernel<16, true, LCBI_WIN_NT>, smem))) return rc;
+      win_attn_fwd_kernel<16, true, LCBI_WIN_NT><<<grid, LCBI_WIN_NT, smem, stream>>>(p);
+    } else {
+      if ((rc = set_smem(win_attn_fwd_kernel<16, true>, smem))) return rc;
+      win_attn_fwd_kernel<16, true><<<grid, 128, smem, stream>>>(p);
+    }
   } else if (p.g.n <= 64) {
     if ((rc = set_smem(win_attn_fwd_kernel<32, true>, smem))) return rc;
     win_attn_fwd_kernel<32, true><<<grid, 128, smem, stream>>>(p);
   } else {
-    if ((rc = set_smem(win_attn_fwd_kernel<32, false>, smem))) return rc;
-    win_attn_fwd_kernel<32, false><<<grid, 128, smem, stream>>>(p);
+    if ((rc = set_smem(win_attn_fwd_kernel<32, false, LCBI_WIN_NT>, smem))) return rc;
+    win_attn_fwd_kernel<32, false, LCBI_WIN_NT><<<grid, LCBI_WIN_NT, smem, stream>>>(p);
   }
   return set_cuda_error(cudaGetLastError());
 }
@@ -750,14 +811,19 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
     const size_t smem = dkdv_smem_bytes(p.g, D);
     dim3 grid(p.win_count, p.H);
     if (D == 16) {
-      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16, true>, smem))) return rc;
-      win_attn_bwd_dkdv_kernel<16, true><<<grid, 128, smem, stream>>>(p);
+      if (p.g.n > 128) {
+        if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16, true, LCBI_WIN_NT>, smem))) return rc;
+        win_attn_bwd_dkdv_kernel<16, true, LCBI_WIN_NT><<<grid, LCBI_WIN_NT, smem, stream>>>(p);
+      } else {
+        if ((rc = set_smem(win_attn_bwd_dkdv_kernel<16, true>, smem))) return rc;
+        win_attn_bwd_dkdv_kernel<16, true><<<grid, 128, smem, stream>>>(p);
+      }
     } else if (p.g.n <= 64) {
       if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32, true>, smem))) return rc;
       win_attn_bwd_dkdv_kernel<32, true><<<grid, 128, smem, stream>>>(p);
     } else {
-      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32, false>, smem))) return rc;
-      win_attn_bwd_dkdv_kernel<32, false><<<grid, 128, smem, stream>>>(p);
+      if ((rc = set_smem(win_attn_bwd_dkdv_kernel<32, false, LCBI_WIN_NT>, smem))) return rc;
+      win_attn_bwd_dkdv_kernel<32, false, LCBI_WIN_NT><<<grid, LCBI_WIN_NT, smem, stream>>>(p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);

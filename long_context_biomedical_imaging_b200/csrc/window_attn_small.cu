@@ -76,7 +76,8 @@ win_attn_fwd_small_kernel(const WinParams p) {
   const int units = p.win_count;
 
   for (int u = blockIdx.x * kWarps + warp; u < units; u += gridDim.x * kWarps) {
-    const int b = (p.win_begin + u) / g.nW, w = (p.win_begin + u) % g.nW;
+    int b, w;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
     // ---- window metadata: two slots per lane
     int first_reg = 0;
     bool differs = false;
@@ -329,7 +330,8 @@ win_attn_bwd_small_kernel(const WinParams p) {
   for (int i = 0; i < D / 8; ++i) pad_dk[i][0] = pad_dk[i][1] = pad_dv[i][0] = pad_dv[i][1] = 0.f;
 
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int b = (p.win_begin + u) / g.nW, w = (p.win_begin + u) % g.nW;
+    int b, w;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
     __syncthreads();                                // previous window fully consumed (and tab / terms written)
     if (tid < 64) {
       int tok = -2, reg = -1;

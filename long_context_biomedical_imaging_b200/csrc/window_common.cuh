@@ -13,6 +13,34 @@
 
 namespace lcbi {
 
+// Division by a runtime-constant divisor as multiply-high + shift (dividend < 2^31): the per-slot index maps below
+// unravel slot and window numbers along three axes, and plain runtime integer division made that ~20 % of all
+// instructions of the window kernels (ncu source view, profiles/r01_ncu_swin4_bwd_hotlines.txt).
+struct FastDiv {
+  uint32_t mul, shr, div;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.div = static_cast<uint32_t>(d);
+  if (d <= 1) {
+    f.mul = 0; f.shr = 0;
+    return f;
+  }
+  uint32_t lg = 0;
+  while ((1u << lg) < static_cast<uint32_t>(d)) ++lg;      // ceil(log2 d)
+  const uint32_t p = 31 + lg;
+  f.mul = static_cast<uint32_t>(((1ull << p) + static_cast<uint32_t>(d) - 1) / static_cast<uint32_t>(d));
+  f.shr = p - 32;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int x, const FastDiv& f) {
+  return f.div == 1 ? x : static_cast<int>(__umulhi(static_cast<uint32_t>(x), f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fdivmod(int x, const FastDiv& f, int& q, int& r) {
+  q = fdiv(x, f);
+  r = x - q * static_cast<int>(f.div);
+}
+
 struct WinGeom {
   int grid[3];      // un-padded token grid (D,H,W); D == 1 for 2-D
   int win[3];       // window actually used (clamped to the grid)
@@ -24,6 +52,7 @@ struct WinGeom {
   int nW;           // windows per image
   int T;            // tokens per image
   int tab_rows;     // prod(2*ctor-1)
+  FastDiv d_win[3], d_ctor[3], d_nwin[3], d_nW;   // divisors of the index maps
 };
 
 // host: fills g from (grid, constructor window, constructor shift); ndim 2 or 3 (2-D gets a leading 1)
@@ -52,13 +81,22 @@ inline int fill_win_geom(WinGeom& g, int ndim, const int* grid, const int* windo
     g.T *= g.grid[k];
     g.tab_rows *= 2 * g.ctor[k] - 1;
   }
+  for (int k = 0; k < 3; ++k) {
+    g.d_win[k] = make_fastdiv(g.win[k]);
+    g.d_ctor[k] = make_fastdiv(g.ctor[k]);
+    g.d_nwin[k] = make_fastdiv(g.nwin[k]);
+  }
+  g.d_nW = make_fastdiv(g.nW);
   return 0;
 }
 
 // token index feeding (window w, slot s), -1 for a zero-pad token; also the shift-mask region id of the slot
 __device__ __forceinline__ void slot_lookup(const WinGeom& g, int w, int s, int& tok, int& region) {
-  const int w2 = w % g.nwin[2], w1 = (w / g.nwin[2]) % g.nwin[1], w0 = w / (g.nwin[2] * g.nwin[1]);
-  const int t2 = s % g.win[2], t1 = (s / g.win[2]) % g.win[1], t0 = s / (g.win[2] * g.win[1]);
+  int w0, w1, w2, t0, t1, t2, q;
+  fdivmod(w, g.d_nwin[2], q, w2);
+  fdivmod(q, g.d_nwin[1], w0, w1);
+  fdivmod(s, g.d_win[2], q, t2);
+  fdivmod(q, g.d_win[1], t0, t1);
   const int wc[3] = {w0, w1, w2}, tc[3] = {t0, t1, t2};
   int src[3];
   bool inside = true;
@@ -78,7 +116,9 @@ __device__ __forceinline__ void slot_lookup(const WinGeom& g, int w, int s, int&
 
 // relative-position index = row_term(i) - col_term(j), slots unravelled in the CONSTRUCTOR window
 __device__ __forceinline__ void relpos_terms(const WinGeom& g, int s, int& row_term, int& col_term) {
-  const int c2 = s % g.ctor[2], c1 = (s / g.ctor[2]) % g.ctor[1], c0 = s / (g.ctor[2] * g.ctor[1]);
+  int c0, c1, c2, q;
+  fdivmod(s, g.d_ctor[2], q, c2);
+  fdivmod(q, g.d_ctor[1], c0, c1);
   const int st1 = 2 * g.ctor[2] - 1, st0 = st1 * (2 * g.ctor[1] - 1);
   col_term = c0 * st0 + c1 * st1 + c2;
   row_term = col_term + (g.ctor[0] - 1) * st0 + (g.ctor[1] - 1) * st1 + (g.ctor[2] - 1);

@@ -6,6 +6,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from long_context_biomedical_imaging_b200 import _lib
+if os.environ.get('LCBI_LIB'):
+    _lib.LIB_PATH = os.environ['LCBI_LIB']   # timing experiments with variant builds
 from long_context_biomedical_imaging_b200 import ops  # noqa: E402
 
 CASES = [
