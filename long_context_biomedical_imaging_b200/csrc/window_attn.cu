@@ -65,31 +65,45 @@ __device__ __forceinline__ bool window_has_mask(const WinGeom& g, const WinMeta&
   return __syncthreads_or(differs) != 0;
 }
 
-// loads rows [row_begin, row_end) of one of q/k/v (or dO when sel == 3) for (batch b, head h) into a smem tile
+// loads rows [row_begin, row_end) of one of q/k/v (or dO when sel == 3) for (batch b, head h) into a smem tile.
+// Four 16-byte gathers are issued per thread before any of them is stored, so a thread pays one global-memory
+// latency per four chunks instead of one per chunk (the loop has a runtime trip count and is not unrolled otherwise).
 template <int D>
 __device__ __forceinline__ void load_rows(uint8_t* tile, const WinParams& p, const int* tok, int b, int h, int sel,
                                           int row_begin, int row_end, int tid, int nthreads) {
   constexpr int kChunks = D / 8;   // 16-byte chunks per row
+  constexpr int kBatch = 4;
   const int total = (row_end - row_begin) * kChunks;
-  for (int e = tid; e < total; e += nthreads) {
-    const int r = row_begin + e / kChunks, c = e % kChunks;
-    const int t = tok[r];
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (t >= 0) {
-      const __nv_bfloat16* src;
-      if (sel < 3)
-        src = p.qkv + ((static_cast<int64_t>(b) * p.g.T + t) * 3 + sel) * p.C + h * D + c * 8;
-      else
-        src = p.d_out + (static_cast<int64_t>(b) * p.g.T + t) * p.C + h * D + c * 8;
-      val = *reinterpret_cast<const uint4*>(src);
-    } else if (t == -1 && sel < 3 && p.qkv_bias != nullptr) {
-      const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
-      val.x = pack2_bf16(bsrc[0], bsrc[1]);
-      val.y = pack2_bf16(bsrc[2], bsrc[3]);
-      val.z = pack2_bf16(bsrc[4], bsrc[5]);
-      val.w = pack2_bf16(bsrc[6], bsrc[7]);
+  const int64_t plane = sel < 3 ? static_cast<int64_t>(3) * p.C : p.C;           // elements per token
+  const __nv_bfloat16* base = (sel < 3 ? p.qkv + sel * p.C : p.d_out) + static_cast<int64_t>(b) * p.g.T * plane + h * D;
+  for (int e0 = tid; e0 < total; e0 += kBatch * nthreads) {
+    uint4 val[kBatch];
+    int tk[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + u * nthreads;
+      val[u] = make_uint4(0u, 0u, 0u, 0u);
+      tk[u] = -2;
+      if (e < total) {
+        const int r = row_begin + e / kChunks, c = e % kChunks;
+        tk[u] = tok[r];
+        if (tk[u] >= 0) val[u] = __ldg(reinterpret_cast<const uint4*>(base + tk[u] * plane + c * 8));
+      }
     }
-    *reinterpret_cast<uint4*>(tile + r * Tile<D>::kStride + c * 16) = val;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + u * nthreads;
+      if (e >= total) continue;
+      const int r = row_begin + e / kChunks, c = e % kChunks;
+      if (tk[u] == -1 && sel < 3 && p.qkv_bias != nullptr) {
+        const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+        val[u].x = pack2_bf16(bsrc[0], bsrc[1]);
+        val[u].y = pack2_bf16(bsrc[2], bsrc[3]);
+        val[u].z = pack2_bf16(bsrc[4], bsrc[5]);
+        val[u].w = pack2_bf16(bsrc[6], bsrc[7]);
+      }
+      *reinterpret_cast<uint4*>(tile + r * Tile<D>::kStride + c * 16) = val[u];
+    }
   }
 }
 
@@ -100,7 +114,7 @@ __device__ __forceinline__ void load_rows(uint8_t* tile, const WinParams& p, con
 // key chunk (n <= 64: the kernel is latency-bound, 235 -> 192 us at cfg2 stage 1) and for d = 16; a loss for
 // d = 32 with 343-token windows, where the spills land in the six-iteration key loop.
 template <int D, bool kHighOcc, int NT = 128>
-__global__ void __launch_bounds__(NT, kHighOcc ? (NT == 128 ? 6 : (NT == 256 ? 3 : 2)) : 1)
+__global__ void __launch_bounds__(NT, kHighOcc ? (NT == 128 ? 6 : (NT == 256 ? 3 : 2)) : (NT == 256 ? 2 : 1))
 win_attn_fwd_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const WinGeom& g = p.g;
@@ -831,7 +845,9 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
   // 3. dQ (+ bias-table gradient): 64-row slabs (4 query tiles) up to 384-token windows, 32-row slabs above
   {
     const int n_ks = round_up(p.g.n, kKeySplit) / kKeySplit;
-    const int qt = (n_ks <= 3) ? 4 : 2;
+    // 64-row slabs (one 384-thread CTA per SM) win when there are many windows to stream through a CTA; with few
+    // windows (late stages: 27 and 8 per image) twice as many 32-row CTAs fill the machine better (measured)
+    const int qt = (n_ks <= 3 && p.win_count > 64) ? 4 : 2;
     const int slab_rows = 16 * qt;
     const size_t smem = dq_smem_bytes(p.g, D, slab_rows);
     const int n_slabs = (p.g.n + slab_rows - 1) / slab_rows;
