@@ -35,6 +35,12 @@ namespace {
 // -------------------------------------------------------------------------------------------------
 // per-CTA window metadata in shared memory
 // -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 struct WinMeta {
   int* tok;        // [n_pad] token index, -1 pad token, -2 slot beyond the window
   int* reg;        // [n_pad] region id
@@ -51,8 +57,8 @@ __device__ __forceinline__ void fill_meta(const WinGeom& g, int w, int n_pad, Wi
     }
     m.tok[s] = tok;
     m.reg[s] = region;
-    m.row_term[s] = rt;
-    m.col_term[s] = ct;
+    m.row_term[s] = rt * 4;     // BYTE offsets into the per-head bias table: the gather address is then
+    m.col_term[s] = ct * 4;     // (table base + row_term) - col_term, one integer add per element
   }
 }
 
@@ -157,7 +163,8 @@ win_attn_fwd_kernel(const WinParams p) {
 #pragma unroll
     for (int kk = 0; kk < D / 16; ++kk) load_a_frag<kStride>(aq[kk], q_base, row0, kk * 16, lane);
     const int i0 = row0 + gq, i1 = i0 + 8;
-    const int rt0 = meta.row_term[i0], rt1 = meta.row_term[i1];
+    const uint32_t tab_base = static_cast<uint32_t>(__cvta_generic_to_shared(tab));
+    const uint32_t tb0 = tab_base + meta.row_term[i0], tb1 = tab_base + meta.row_term[i1];   // table row addresses
     const int rg0 = meta.reg[i0], rg1 = meta.reg[i1];
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float oacc[D / 8][4];
@@ -189,8 +196,8 @@ win_attn_fwd_kernel(const WinParams p) {
           const int2 ct = *reinterpret_cast<const int2*>(meta.col_term + j);
           int2 rj = make_int2(0, 0);
           if (kMasked) rj = *reinterpret_cast<const int2*>(meta.reg + j);
-          float v00 = fmaf(s[nt][0], p.scale_log2, tab[rt0 - ct.x]), v01 = fmaf(s[nt][1], p.scale_log2, tab[rt0 - ct.y]);
-          float v10 = fmaf(s[nt][2], p.scale_log2, tab[rt1 - ct.x]), v11 = fmaf(s[nt][3], p.scale_log2, tab[rt1 - ct.y]);
+          float v00 = fmaf(s[nt][0], p.scale_log2, lds_f32(tb0 - ct.x)), v01 = fmaf(s[nt][1], p.scale_log2, lds_f32(tb0 - ct.y));
+          float v10 = fmaf(s[nt][2], p.scale_log2, lds_f32(tb1 - ct.x)), v11 = fmaf(s[nt][3], p.scale_log2, lds_f32(tb1 - ct.y));
           if (kMasked) {
             v00 += rg0 != rj.x ? mask_log2 : 0.f; v01 += rg0 != rj.y ? mask_log2 : 0.f;
             v10 += rg1 != rj.x ? mask_log2 : 0.f; v11 += rg1 != rj.y ? mask_log2 : 0.f;
@@ -390,7 +397,8 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
       load_a_frag<kStride>(av[kk], v_base, key0, kk * 16, lane);
     }
     const int j0 = key0 + gq, j1 = j0 + 8;           // key rows held by this thread
-    const int ct0 = meta.col_term[j0], ct1 = meta.col_term[j1];
+    const uint32_t tab_base = static_cast<uint32_t>(__cvta_generic_to_shared(tab));
+    const uint32_t tc0 = tab_base - meta.col_term[j0], tc1 = tab_base - meta.col_term[j1];
     const int rg0 = meta.reg[j0], rg1 = meta.reg[j1];
     const bool kv0 = j0 < n, kv1 = j1 < n;
     float dk[D / 8][4], dv[D / 8][4];
@@ -422,8 +430,8 @@ win_attn_bwd_dkdv_kernel(const WinParams p) {
           for (int e = 0; e < 2; ++e) {
             const float4 qc4 = qcol[qc + nt * 8 + qq * 2 + e];    // query (column of the transposed tile): lse2, dsum, rt, region
             const int rt = __float_as_int(qc4.z);
-            float l0 = fmaf(st[nt][e], p.scale_log2, tab[rt - ct0]) - qc4.x;
-            float l1 = fmaf(st[nt][2 + e], p.scale_log2, tab[rt - ct1]) - qc4.x;
+            float l0 = fmaf(st[nt][e], p.scale_log2, lds_f32(tc0 + rt)) - qc4.x;
+            float l1 = fmaf(st[nt][2 + e], p.scale_log2, lds_f32(tc1 + rt)) - qc4.x;
             if (kMasked) {
               const int ri = __float_as_int(qc4.w);
               l0 += ri != rg0 ? mask_log2 : 0.f;
@@ -610,7 +618,8 @@ win_attn_bwd_dq_kernel(const WinParams p) {
     const int r0 = qt * 16 + gq, r1 = r0 + 8;                 // rows inside the slab
     const int i0 = row_base + r0, i1 = row_base + r1;         // window slots
     const float lse0 = s_lse[r0], lse1 = s_lse[r1], ds0 = s_dsum[r0], ds1 = s_dsum[r1];
-    const int rt0 = meta.row_term[i0], rt1 = meta.row_term[i1];
+    const uint32_t tab_base = static_cast<uint32_t>(__cvta_generic_to_shared(tab));
+    const uint32_t tb0 = tab_base + meta.row_term[i0], tb1 = tab_base + meta.row_term[i1];
     const int rg0 = meta.reg[i0], rg1 = meta.reg[i1];
     float dq[D / 8][4];
 #pragma unroll
@@ -647,8 +656,8 @@ win_attn_bwd_dq_kernel(const WinParams p) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int cte = e ? ct.y : ct.x;
-            float l0 = fmaf(s[nt][e], p.scale_log2, tab[rt0 - cte]) - lse0;
-            float l1 = fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - cte]) - lse1;
+            float l0 = fmaf(s[nt][e], p.scale_log2, lds_f32(tb0 - cte)) - lse0;
+            float l1 = fmaf(s[nt][2 + e], p.scale_log2, lds_f32(tb1 - cte)) - lse1;
             if (kMasked) {
               const int rje = e ? rj.y : rj.x;
               l0 += rg0 != rje ? mask_log2 : 0.f;
