@@ -272,7 +272,9 @@ struct SmallBwdSmem {
   static constexpr int kStride = Tile<D>::kStride;
   static constexpr int kTileBytes = 64 * kStride;
   static constexpr int kPBytes = 64 * kPStride;
-  static constexpr int kTotal = 4 * kTileBytes + 2 * kPBytes + 2 * 64 * 4 /*lse, dsum*/ + 4 * 64 * 4 /*meta*/;
+  // q / k / v / dO tiles and the per-window metadata (token, region, lse, dsum) are double-buffered: the next window
+  // is gathered with cp.async while the current one is processed
+  static constexpr int kTotal = 2 * 4 * kTileBytes + 2 * kPBytes + 2 * 4 * 64 * 4 /*meta x2*/ + 2 * 64 * 4 /*rt, ct*/ + 16;
 };
 
 template <int D>
@@ -287,19 +289,14 @@ win_attn_bwd_small_kernel(const WinParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.y;
 
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + L::kTileBytes;
-  uint8_t* sV = sK + L::kTileBytes;
-  uint8_t* sDO = sV + L::kTileBytes;
-  uint8_t* sP = sDO + L::kTileBytes;
+  uint8_t* tiles = smem;                               // [2][4][kTileBytes]: q, k, v, dO of the current / next window
+  uint8_t* sP = tiles + 2 * 4 * L::kTileBytes;
   uint8_t* sDS = sP + L::kPBytes;
-  float* s_lse = reinterpret_cast<float*>(sDS + L::kPBytes);
-  float* s_dsum = s_lse + 64;
-  int* s_tok = reinterpret_cast<int*>(s_dsum + 64);
-  int* s_reg = s_tok + 64;
-  int* s_rt = s_reg + 64;
+  float* s_meta = reinterpret_cast<float*>(sDS + L::kPBytes);   // [2][4][64]: lse, dsum, tok, region
+  int* s_rt = reinterpret_cast<int*>(s_meta + 2 * 4 * 64);
   int* s_ct = s_rt + 64;
-  float* tab = reinterpret_cast<float*>(s_ct + 64);   // [tab_rows] bias table column of this head, x log2e
+  int* s_pad = s_ct + 64;                              // [2] (+2 unused): does the window hold pad tokens?
+  float* tab = reinterpret_cast<float*>(s_pad + 4);    // [tab_rows] bias table column of this head, x log2e
 
   for (int t = tid; t < g.tab_rows; t += 128) tab[t] = p.table[static_cast<int64_t>(t) * p.H + h] * kLog2e;
   if (tid < 64) {
@@ -309,10 +306,7 @@ win_attn_bwd_small_kernel(const WinParams p) {
     s_ct[tid] = ct;
   }
 
-  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
-  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
-  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
-  const uint32_t do_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDO));
+  const uint32_t tiles_base = static_cast<uint32_t>(__cvta_generic_to_shared(tiles));
   const uint32_t p_base = static_cast<uint32_t>(__cvta_generic_to_shared(sP));
   const uint32_t ds_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDS));
   const int gq = lane >> 2, qq = lane & 3;
@@ -329,48 +323,93 @@ win_attn_bwd_small_kernel(const WinParams p) {
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) pad_dk[i][0] = pad_dk[i][1] = pad_dv[i][0] = pad_dv[i][1] = 0.f;
 
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+  // ---- per-window gather pipeline -----------------------------------------------------------------------------
+  // window_meta: slot -> token / region (closed form) and the token's lse / dsum, for one window, by threads 0-63;
+  // issue_tiles: cp.async of the window's q / k / v / dO rows (zero-fill for pad and dead rows).
+  struct MetaRegs { int tok, reg; float lse, dsum; };
+  auto window_meta = [&](int u) {
+    MetaRegs m{-2, -1, INFINITY, 0.f};              // pad / dead query rows: P = exp2(. - inf) = 0
     int b, w;
     fdivmod(p.win_begin + u, g.d_nW, b, w);
-    __syncthreads();                                // previous window fully consumed (and tab / terms written)
-    if (tid < 64) {
-      int tok = -2, reg = -1;
-      if (tid < n) slot_lookup(g, w, tid, tok, reg);
-      s_tok[tid] = tok;
-      s_reg[tid] = reg;
-      float l = INFINITY, d = 0.f;                  // pad / dead query rows: P = exp2(. - inf) = 0
-      if (tok >= 0) {
-        const int64_t idx = (static_cast<int64_t>(b) * g.T + tok) * p.H + h;
-        l = p.lse2[idx];
-        d = p.dsum[idx];
-      }
-      s_lse[tid] = l;
-      s_dsum[tid] = d;
+    if (tid < n) slot_lookup(g, w, tid, m.tok, m.reg);
+    if (m.tok >= 0) {
+      const int64_t idx = (static_cast<int64_t>(b) * g.T + m.tok) * p.H + h;
+      m.lse = __ldg(p.lse2 + idx);
+      m.dsum = __ldg(p.dsum + idx);
     }
-    __syncthreads();
-    {
-      const int64_t tok_base = static_cast<int64_t>(b) * g.T;
+    return m;
+  };
+  auto store_meta = [&](const MetaRegs& m, int buf) {     // threads 0-63
+    float* mb = s_meta + buf * 4 * 64;
+    mb[tid] = m.lse;
+    mb[64 + tid] = m.dsum;
+    reinterpret_cast<int*>(mb)[128 + tid] = m.tok;
+    reinterpret_cast<int*>(mb)[192 + tid] = m.reg;
+    const unsigned pads = __ballot_sync(0xffffffffu, m.tok == -1);
+    if (lane == 0 && pads) atomicOr(&s_pad[buf], 1);
+  };
+  auto issue_tiles = [&](int u, int buf) {
+    int b, w;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
+    const int64_t tok_base = static_cast<int64_t>(b) * g.T;
+    const int* tk = reinterpret_cast<const int*>(s_meta + buf * 4 * 64) + 128;
 #pragma unroll 4
-      for (int e = tid; e < 4 * 64 * kChunks; e += 128) {
-        const int sel = e / (64 * kChunks);          // 0 q, 1 k, 2 v, 3 dO
-        const int r = (e / kChunks) & 63, c = e % kChunks;
-        const int t = s_tok[r];
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0) {
-          const __nv_bfloat16* src = sel < 3 ? p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8
-                                             : p.d_out + (tok_base + t) * p.C + h * D + c * 8;
-          val = *reinterpret_cast<const uint4*>(src);
-        } else if (t == -1 && sel < 3 && p.qkv_bias != nullptr) {
-          const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
-          val.x = pack2_bf16(bsrc[0], bsrc[1]);
-          val.y = pack2_bf16(bsrc[2], bsrc[3]);
-          val.z = pack2_bf16(bsrc[4], bsrc[5]);
-          val.w = pack2_bf16(bsrc[6], bsrc[7]);
-        }
-        *reinterpret_cast<uint4*>(smem + sel * L::kTileBytes + r * kStride + c * 16) = val;
+    for (int e = tid; e < 4 * 64 * kChunks; e += 128) {
+      const int sel = e / (64 * kChunks);            // 0 q, 1 k, 2 v, 3 dO
+      const int r = (e / kChunks) & 63, c = e % kChunks;
+      const int t = tk[r];
+      const __nv_bfloat16* src = p.qkv;              // any valid address when nothing is read (zero fill)
+      if (t >= 0)
+        src = sel < 3 ? p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8
+                      : p.d_out + (tok_base + t) * p.C + h * D + c * 8;
+      const uint32_t dst = tiles_base + (buf * 4 + sel) * L::kTileBytes + r * kStride + c * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(t >= 0 ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (tid < 4) s_pad[tid] = 0;
+  __syncthreads();                                  // tab / terms / flags written
+  if (static_cast<int>(blockIdx.x) < units) {
+    if (tid < 64) store_meta(window_meta(blockIdx.x), 0);
+    __syncthreads();
+    issue_tiles(blockIdx.x, 0);
+  }
+
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    const int u_next = u + gridDim.x;
+    int b, w;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
+    const float* s_lse = s_meta + cur * 4 * 64;
+    const float* s_dsum = s_lse + 64;
+    const int* s_tok = reinterpret_cast<const int*>(s_lse) + 128;
+    const int* s_reg = s_tok + 64;
+    uint8_t* sQ = tiles + (cur * 4 + 0) * L::kTileBytes;
+    const uint32_t q_base = tiles_base + (cur * 4 + 0) * L::kTileBytes, k_base = q_base + L::kTileBytes;
+    const uint32_t v_base = k_base + L::kTileBytes, do_base = v_base + L::kTileBytes;
+
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (s_pad[cur] && p.qkv_bias != nullptr) {
+      // pad tokens enter the reference as zeros before the qkv Linear, so their q / k / v rows are the Linear's bias
+      for (int e = tid; e < 3 * 64 * kChunks; e += 128) {
+        const int sel = e / (64 * kChunks), r = (e / kChunks) & 63, c = e % kChunks;
+        if (s_tok[r] != -1) continue;
+        const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+        uint4 val;
+        val.x = pack2_bf16(bsrc[0], bsrc[1]);
+        val.y = pack2_bf16(bsrc[2], bsrc[3]);
+        val.z = pack2_bf16(bsrc[4], bsrc[5]);
+        val.w = pack2_bf16(bsrc[6], bsrc[7]);
+        *reinterpret_cast<uint4*>(sQ + sel * L::kTileBytes + r * kStride + c * 16) = val;
       }
     }
-    __syncthreads();
+    if (tid == 0) s_pad[nxt] = 0;                   // (last read one iteration ago; set again after the barrier)
+    __syncthreads();                                // this window's tiles are in; the previous window is fully consumed
+    // the next window's metadata: the two dependent global loads stay in flight during phase 1
+    MetaRegs next_meta{-2, -1, INFINITY, 0.f};
+    if (u_next < units && tid < 64) next_meta = window_meta(u_next);
 
     // ------------------------------------------------------------ phase 1: this warp's query tile
     if (tile_live) {
@@ -460,7 +499,9 @@ win_attn_bwd_small_kernel(const WinParams p) {
         reinterpret_cast<uint32_t*>(sDS + row0 * kPStride)[e] = 0u;
       }
     }
-    __syncthreads();
+    if (u_next < units && tid < 64) store_meta(next_meta, nxt);
+    __syncthreads();                                // P / dS tiles complete; next window's metadata visible
+    if (u_next < units) issue_tiles(u_next, nxt);   // lands while phase 2 runs and the loop turns around
 
     // ------------------------------------------------------------ phase 2: this warp's key tile
     if (tile_live) {
