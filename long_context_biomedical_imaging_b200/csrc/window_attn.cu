@@ -786,10 +786,11 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
   WinParams p;
   int rc = fill_params(p, a);
   if (rc) return rc;
-  // experimental warp-per-window persistent kernel for <= 64-token windows (window_attn_small.cu); measured slower
-  // than the CTA-per-(window, head) kernel on B200 (8 warps/SM cannot hide its latency), so it is opt-in
-  static const bool use_small = std::getenv("LCBI_WIN_SMALL") != nullptr;
-  if (use_small && p.g.n <= 64) return win_attn_fwd_small_launch(p, a.head_dim, stream);
+  // <= 64-token windows with enough of them to stream: persistent kernel with the bias tile in registers and cp.async
+  // double buffering (window_attn_small.cu; cfg2 stage 1: 161 -> 119 us). With few windows (late stages) the
+  // CTA-per-(window, head) kernel below fills the machine better (measured).
+  static const bool legacy_small_fwd = std::getenv("LCBI_WIN_LEGACY_FWD") != nullptr;
+  if (p.g.n <= 64 && p.win_count >= 1024 && !legacy_small_fwd) return win_attn_fwd_small_launch(p, a.head_dim, stream);
   const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
   dim3 grid(p.win_count, p.H);
   if (a.head_dim == 16) {

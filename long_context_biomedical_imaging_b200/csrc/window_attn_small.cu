@@ -19,117 +19,145 @@ namespace lcbi {
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kBiasStride = 72;   // floats per bias-tile row: 8-byte loads of a quad pattern hit 16 distinct bank pairs
-
+// =================================================================================================
+// Forward for small windows (<= 64 tokens: every 2-D config): persistent CTA = (head, slice of the window list),
+// 4 warps = the four 16-row query tiles of a window.
+//   * the head's relative-position bias tile lives in REGISTERS (32 values per thread, x log2e, -inf in dead key
+//     columns) for the whole kernel: no table gathers and no bounds checks per logit;
+//   * the q / k / v rows and the slot -> token map of the NEXT window are gathered with cp.async into a second
+//     buffer while the current window is processed (the CTA-per-(window, head) kernel exposed one global-memory
+//     round trip per window);
+//   * the -100 shift-mask term is evaluated only for windows that straddle a region boundary.
+// =================================================================================================
 template <int D>
-struct SmallSmem {
+struct SmallFwdSmem {
   static constexpr int kStride = Tile<D>::kStride;
   static constexpr int kTileBytes = 64 * kStride;
-  static constexpr int kPerWarp = 3 * kTileBytes + 2 * 64 * 4;   // Q, K, V tiles + tok[64] + reg[64]
-  static constexpr int kBiasBytes = 64 * kBiasStride * 4;
-  static constexpr int kTotal = kBiasBytes + kWarps * kPerWarp;
+  static constexpr int kTotal = 2 * 3 * kTileBytes + 2 * 2 * 64 * 4 /*tok, reg x2*/ + 16 /*flags*/;
 };
 
 template <int D>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(128, 4)
 win_attn_fwd_small_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  using L = SmallSmem<D>;
+  using L = SmallFwdSmem<D>;
   constexpr int kStride = L::kStride;
   constexpr int kChunks = D / 8;
   const WinGeom& g = p.g;
   const int n = g.n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.y;
-
-  float* bias = reinterpret_cast<float*>(smem);
-  uint8_t* wbase = smem + L::kBiasBytes + warp * L::kPerWarp;
-  uint8_t* sQ = wbase;
-  uint8_t* sK = sQ + L::kTileBytes;
-  uint8_t* sV = sK + L::kTileBytes;
-  int* s_tok = reinterpret_cast<int*>(sV + L::kTileBytes);
-  int* s_reg = s_tok + 64;
-
-  // ---- per-CTA: expand relative_position_bias_table[index[i, j], h] * log2e into the bias tile
-  for (int e = tid; e < 64 * 64; e += kWarps * 32) {
-    const int i = e >> 6, j = e & 63;
-    float v = 0.f;
-    if (j >= n) {
-      v = -INFINITY;
-    } else if (i < n) {
-      int rt, ct, rt2, ct2;
-      relpos_terms(g, i, rt, ct);
-      relpos_terms(g, j, rt2, ct2);
-      v = p.table[static_cast<int64_t>(rt - ct2) * p.H + h] * kLog2e;
-    }
-    bias[i * kBiasStride + j] = v;
-  }
-  __syncthreads();
-
-  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
-  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
-  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
   const int gq = lane >> 2, qq = lane & 3;
-  const float mask_log2 = -100.0f * kLog2e;
-  const int n_qt = (n + 15) / 16;
+
+  uint8_t* tiles = smem;                                       // [2][3][kTileBytes]: q, k, v
+  int* s_meta = reinterpret_cast<int*>(tiles + 2 * 3 * L::kTileBytes);   // [2][2][64]: tok, region
+  int* s_flags = s_meta + 2 * 2 * 64;                          // [2]: bit 0 pad tokens present, bit 1 mask needed
+  const uint32_t tiles_base = static_cast<uint32_t>(__cvta_generic_to_shared(tiles));
+
   const int units = p.win_count;
+  const int row0 = warp * 16;
+  const bool tile_live = row0 < n;
+  const int i0 = row0 + gq, i1 = i0 + 8;
+  const float mask_log2 = -100.0f * kLog2e;
 
-  for (int u = blockIdx.x * kWarps + warp; u < units; u += gridDim.x * kWarps) {
-    int b, w;
-    fdivmod(p.win_begin + u, g.d_nW, b, w);
-    // ---- window metadata: two slots per lane
-    int first_reg = 0;
-    bool differs = false;
+  // bias[h, i, j] * log2e of this thread's fragment positions; dead key columns read -inf, dead rows 0
+  float bias[8][4];
+  {
+    int rt0 = 0, rt1 = 0, dummy;
+    if (i0 < n) relpos_terms(g, i0, rt0, dummy);
+    if (i1 < n) relpos_terms(g, i1, rt1, dummy);
 #pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      const int s = lane + rep * 32;
-      int tok = -2, reg = -1;
-      if (s < n) slot_lookup(g, w, s, tok, reg);
-      s_tok[s] = tok;
-      s_reg[s] = reg;
-      if (rep == 0) first_reg = __shfl_sync(0xffffffffu, reg, 0);
-      differs = differs || (s < n && reg != first_reg);
-    }
-    const bool has_mask = __any_sync(0xffffffffu, differs);
-    __syncwarp();
-
-    // ---- gather q, k, v rows of this (window, head): 16-byte chunks, pad tokens take the qkv bias
-    {
-      const int64_t tok_base = static_cast<int64_t>(b) * g.T;
-#pragma unroll 4
-      for (int e = lane; e < 3 * 64 * kChunks; e += 32) {
-        const int sel = e / (64 * kChunks);
-        const int r = (e / kChunks) & 63, c = e % kChunks;
-        const int t = s_tok[r];
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0) {
-          val = *reinterpret_cast<const uint4*>(p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8);
-        } else if (t == -1 && p.qkv_bias != nullptr) {
-          const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
-          val.x = pack2_bf16(bsrc[0], bsrc[1]);
-          val.y = pack2_bf16(bsrc[2], bsrc[3]);
-          val.z = pack2_bf16(bsrc[4], bsrc[5]);
-          val.w = pack2_bf16(bsrc[6], bsrc[7]);
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + qq * 2 + e;
+        float v0 = -INFINITY, v1 = -INFINITY;
+        if (j < n) {
+          int rtj, ctj;
+          relpos_terms(g, j, rtj, ctj);
+          v0 = i0 < n ? __ldg(p.table + static_cast<int64_t>(rt0 - ctj) * p.H + h) * kLog2e : 0.f;
+          v1 = i1 < n ? __ldg(p.table + static_cast<int64_t>(rt1 - ctj) * p.H + h) * kLog2e : 0.f;
         }
-        *reinterpret_cast<uint4*>(wbase + sel * L::kTileBytes + r * kStride + c * 16) = val;
+        bias[nt][e] = v0;
+        bias[nt][2 + e] = v1;
       }
     }
-    __syncwarp();
+  }
 
-    // ---- K^T and V fragments for the whole window, kept in registers across the query tiles
-    uint32_t kf[8][D / 16][2], vf[4][D / 8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk) load_b_frag_nt<kStride>(kf[nt][kk][0], kf[nt][kk][1], k_base, nt * 8, kk * 16, lane);
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd) load_b_frag_t<kStride>(vf[kb][nd][0], vf[kb][nd][1], v_base, kb * 16, nd * 8, lane);
+  auto store_meta = [&](int u, int buf) {                     // threads 0-63: one window slot each
+    int b, w, tok = -2, reg = -1, tok0, reg0;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
+    if (tid < n) slot_lookup(g, w, tid, tok, reg);
+    slot_lookup(g, w, 0, tok0, reg0);
+    s_meta[buf * 128 + tid] = tok;
+    s_meta[buf * 128 + 64 + tid] = reg;
+    const unsigned pads = __ballot_sync(0xffffffffu, tok == -1);
+    const unsigned mixed = __ballot_sync(0xffffffffu, tid < n && reg != reg0);
+    if (lane == 0 && (pads | mixed)) atomicOr(&s_flags[buf], (pads ? 1 : 0) | (mixed ? 2 : 0));
+  };
+  auto issue_tiles = [&](int u, int buf) {
+    int b, w;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
+    const int64_t tok_base = static_cast<int64_t>(b) * g.T;
+    const int* tk = s_meta + buf * 128;
+#pragma unroll 4
+    for (int e = tid; e < 3 * 64 * kChunks; e += 128) {
+      const int sel = e / (64 * kChunks);            // 0 q, 1 k, 2 v
+      const int r = (e / kChunks) & 63, c = e % kChunks;
+      const int t = tk[r];
+      const __nv_bfloat16* src = p.qkv;              // any valid address when nothing is read (zero fill)
+      if (t >= 0) src = p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8;
+      const uint32_t dst = tiles_base + (buf * 3 + sel) * L::kTileBytes + r * kStride + c * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(t >= 0 ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
-    for (int qt = 0; qt < n_qt; ++qt) {
-      const int row0 = qt * 16;
+  if (tid < 2) s_flags[tid] = 0;
+  __syncthreads();
+  if (static_cast<int>(blockIdx.x) < units) {
+    if (tid < 64) store_meta(blockIdx.x, 0);
+    __syncthreads();
+    issue_tiles(blockIdx.x, 0);
+  }
+
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    const int u_next = u + gridDim.x;
+    int b, w;
+    fdivmod(p.win_begin + u, g.d_nW, b, w);
+    const int* s_tok = s_meta + cur * 128;
+    const int* s_reg = s_tok + 64;
+    uint8_t* sQ = tiles + (cur * 3) * L::kTileBytes;
+    const uint32_t q_base = tiles_base + (cur * 3) * L::kTileBytes, k_base = q_base + L::kTileBytes;
+    const uint32_t v_base = k_base + L::kTileBytes;
+
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int flags = s_flags[cur];
+    if ((flags & 1) && p.qkv_bias != nullptr) {
+      // pad tokens enter the reference as zeros before the qkv Linear, so their q / k / v rows are the Linear's bias
+      for (int e = tid; e < 3 * 64 * kChunks; e += 128) {
+        const int sel = e / (64 * kChunks), r = (e / kChunks) & 63, c = e % kChunks;
+        if (s_tok[r] != -1) continue;
+        const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+        uint4 val;
+        val.x = pack2_bf16(bsrc[0], bsrc[1]);
+        val.y = pack2_bf16(bsrc[2], bsrc[3]);
+        val.z = pack2_bf16(bsrc[4], bsrc[5]);
+        val.w = pack2_bf16(bsrc[6], bsrc[7]);
+        *reinterpret_cast<uint4*>(sQ + sel * L::kTileBytes + r * kStride + c * 16) = val;
+      }
+    }
+    if (tid == 0) s_flags[nxt] = 0;                 // (last read one iteration ago; set again after the barrier)
+    __syncthreads();                                // this window's tiles are in; the previous window is fully consumed
+    if (u_next < units) {
+      if (tid < 64) store_meta(u_next, nxt);
+      __syncthreads();
+      issue_tiles(u_next, nxt);                     // lands while this window is processed
+    }
+
+    if (tile_live) {
       uint32_t aq[D / 16][4];
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk) load_a_frag<kStride>(aq[kk], q_base, row0, kk * 16, lane);
@@ -138,34 +166,29 @@ win_attn_fwd_small_kernel(const WinParams p) {
       for (int nt = 0; nt < 8; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) mma_bf16_16816(s[nt], aq[kk], kf[nt][kk][0], kf[nt][kk][1]);
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t b0, b1;
+          load_b_frag_nt<kStride>(b0, b1, k_base, nt * 8, kk * 16, lane);
+          mma_bf16_16816(s[nt], aq[kk], b0, b1);
+        }
       }
-      const int i0 = row0 + gq, i1 = i0 + 8;
-      const float* b0p = bias + i0 * kBiasStride + qq * 2;
-      const float* b1p = bias + i1 * kBiasStride + qq * 2;
       float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const float2 bb0 = *reinterpret_cast<const float2*>(b0p + nt * 8);
-        const float2 bb1 = *reinterpret_cast<const float2*>(b1p + nt * 8);
-        s[nt][0] = fmaf(s[nt][0], p.scale_log2, bb0.x);
-        s[nt][1] = fmaf(s[nt][1], p.scale_log2, bb0.y);
-        s[nt][2] = fmaf(s[nt][2], p.scale_log2, bb1.x);
-        s[nt][3] = fmaf(s[nt][3], p.scale_log2, bb1.y);
+        s[nt][0] = fmaf(s[nt][0], p.scale_log2, bias[nt][0]);
+        s[nt][1] = fmaf(s[nt][1], p.scale_log2, bias[nt][1]);
+        s[nt][2] = fmaf(s[nt][2], p.scale_log2, bias[nt][2]);
+        s[nt][3] = fmaf(s[nt][3], p.scale_log2, bias[nt][3]);
       }
-      if (has_mask) {
+      if (flags & 2) {                              // the window straddles a shift-mask region boundary
         const int rg0 = s_reg[i0], rg1 = s_reg[i1];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           const int2 rj = *reinterpret_cast<const int2*>(s_reg + nt * 8 + qq * 2);
-          if (rj.x >= 0) {   // real window slots only (-1 marks the tile padding, already -inf through the bias)
-            if (rg0 != rj.x) s[nt][0] += mask_log2;
-            if (rg1 != rj.x) s[nt][2] += mask_log2;
-          }
-          if (rj.y >= 0) {
-            if (rg0 != rj.y) s[nt][1] += mask_log2;
-            if (rg1 != rj.y) s[nt][3] += mask_log2;
-          }
+          s[nt][0] += rg0 != rj.x ? mask_log2 : 0.f;
+          s[nt][1] += rg0 != rj.y ? mask_log2 : 0.f;
+          s[nt][2] += rg1 != rj.x ? mask_log2 : 0.f;
+          s[nt][3] += rg1 != rj.y ? mask_log2 : 0.f;
         }
       }
 #pragma unroll
@@ -193,17 +216,21 @@ win_attn_fwd_small_kernel(const WinParams p) {
 #pragma unroll
       for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
+      for (int kb = 0; kb < 4; ++kb) {              // 16 keys per step
         uint32_t ap[4];
         ap[0] = pack2_bf16(s[2 * kb][0], s[2 * kb][1]);
         ap[1] = pack2_bf16(s[2 * kb][2], s[2 * kb][3]);
         ap[2] = pack2_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
         ap[3] = pack2_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
 #pragma unroll
-        for (int nd = 0; nd < D / 8; ++nd) mma_bf16_16816(oacc[nd], ap, vf[kb][nd][0], vf[kb][nd][1]);
+        for (int nd = 0; nd < D / 8; ++nd) {
+          uint32_t b0, b1;
+          load_b_frag_t<kStride>(b0, b1, v_base, kb * 16, nd * 8, lane);
+          mma_bf16_16816(oacc[nd], ap, b0, b1);
+        }
       }
       const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-      // stage the 16 x D output tile in this tile's (already consumed) Q rows, then 16-byte scatter stores
+      // stage the 16 x D output tile in this warp's (already consumed) Q rows, then 16-byte scatter stores
       __syncwarp();
 #pragma unroll
       for (int nd = 0; nd < D / 8; ++nd) {
@@ -224,13 +251,12 @@ win_attn_fwd_small_kernel(const WinParams p) {
               *reinterpret_cast<const uint4*>(sQ + r * kStride + c * 16);
       }
     }
-    __syncwarp();   // the next window overwrites this warp's tiles
   }
 }
 
 template <int D>
 int launch_small(const WinParams& p, cudaStream_t stream) {
-  using L = SmallSmem<D>;
+  using L = SmallFwdSmem<D>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(win_attn_fwd_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -238,12 +264,10 @@ int launch_small(const WinParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   const int units = p.win_count;
-  const int ctas_per_sm = (227 * 1024) / (L::kTotal + 1024);
-  int grid_x = (148 * (ctas_per_sm > 0 ? ctas_per_sm : 1) + p.H - 1) / p.H;
-  const int max_x = (units + kWarps - 1) / kWarps;
-  if (grid_x > max_x) grid_x = max_x;
+  int grid_x = (2 * 148 * 4 + p.H - 1) / p.H;     // ~2 waves of persistent CTAs (4 per SM) per head slice
+  if (grid_x > units) grid_x = units;
   if (grid_x < 1) grid_x = 1;
-  win_attn_fwd_small_kernel<D><<<dim3(grid_x, p.H), kWarps * 32, L::kTotal, stream>>>(p);
+  win_attn_fwd_small_kernel<D><<<dim3(grid_x, p.H), 128, L::kTotal, stream>>>(p);
   return set_cuda_error(cudaGetLastError());
 }
 
