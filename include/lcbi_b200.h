@@ -35,6 +35,11 @@ typedef enum lcbi_status {
 #define LCBI_B200_VERSION 100 /* 0.1.0 */
 
 int lcbi_version(void);
+
+/* The dense attention kernels are persistent (one or two CTAs per SM for the whole launch). When a communication
+ * kernel must run BESIDE them (ring K/V exchange over NCCL on a side stream), it needs SMs of its own: the next
+ * launches leave `n` SMs unused (0..64, default 0; process-wide). */
+int lcbi_set_reserved_sms(int n);
 const char* lcbi_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------

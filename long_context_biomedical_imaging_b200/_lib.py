@@ -44,6 +44,7 @@ SIGNATURES = {
     "lcbi_win_attn_bwd_range": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_float] + [c_vp] * 10 +
                                               [ctypes.c_int, ctypes.c_int, c_vp]),
+    "lcbi_set_reserved_sms": (ctypes.c_int, [ctypes.c_int]),
     "lcbi_window_maps": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_i32p, c_i32p, c_vp]),
 }
 

@@ -34,9 +34,20 @@ static void copy3(int64_t* dst, const int64_t* src) {
 
 using namespace lcbi;
 
+static int g_reserved_sms = 0;
+namespace lcbi {
+int reserved_sms() { return g_reserved_sms; }
+}  // namespace lcbi
+
 extern "C" {
 
 int lcbi_version(void) { return LCBI_B200_VERSION; }
+
+int lcbi_set_reserved_sms(int n) {
+  if (n < 0 || n > 64) return fail(LCBI_ERR_BAD_ARG, "lcbi_set_reserved_sms: expected 0..64");
+  g_reserved_sms = n;
+  return LCBI_OK;
+}
 
 const char* lcbi_last_error(void) { return g_err; }
 

@@ -749,7 +749,8 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   }
   p.n_kv_tiles = (a.Nk + kTile - 1) / kTile;
   p.n_items = p.n_kv_tiles * a.H * a.B;
-  dim3 grid(p.n_items < num_sms ? p.n_items : num_sms);
+  const int slots = num_sms - reserved_sms() > 1 ? num_sms - reserved_sms() : 1;
+  dim3 grid(p.n_items < slots ? p.n_items : slots);
   dense_attn_bwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, tdo, tacc, tdk, tdv, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);

@@ -420,7 +420,8 @@ int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream) {
   p.n_items = p.n_q_tiles * a.H * a.B;
   p.scale_log2 = a.scale * kLog2e;
   p.lse = a.lse;
-  dim3 grid(p.n_items < kCtasPerSm * num_sms ? p.n_items : kCtasPerSm * num_sms);
+  const int slots = kCtasPerSm * (num_sms - reserved_sms() > 1 ? num_sms - reserved_sms() : 1);
+  dim3 grid(p.n_items < slots ? p.n_items : slots);
   dense_attn_fwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, to, p);
   return set_cuda_error(cudaGetLastError());
 }

@@ -37,6 +37,9 @@ struct DenseAttnBwdArgs {
 size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
 int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream);
 
+// SMs the persistent dense kernels leave free (for communication kernels running beside them); capi.cu
+int reserved_sms();
+
 // patch embedding (patch_embed.cu). img_dims / patch / grid are (D, H, W)-ordered triples (D = 1 for 2-D).
 int patch_embed_fwd_launch(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
                            void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,

@@ -17,6 +17,9 @@ gloo backend (tests/test_ring_gloo.py); the defaults are the CUDA kernels and th
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -36,10 +39,29 @@ def _cuda_merge(acc, lse_acc, o_s, lse_s, first):
     ops.attn_merge(acc, lse_acc, o_s, lse_s, first)
 
 
+@contextlib.contextmanager
+def _leave_sms_for_comm(comm, device):
+    """The dense kernels are persistent (they hold every SM for a whole launch), so the NCCL send/recv kernels of the
+    side stream may only start once a launch retires. While a ring pass runs, the kernels can leave
+    `comm.reserved_sms` SMs unused (`lcbi_set_reserved_sms`; env LCBI_RING_RESERVED_SMS). Default 0: at 2 GPUs the
+    exchange is small next to a step's compute and giving up SMs only cost time (459.8 ms with 0, 474.1 with 8,
+    490.7 with 16 reserved SMs per cfg5 step)."""
+    n = comm.reserved_sms if (comm.world > 1 and device.type == "cuda") else 0
+    if n:
+        from . import _lib
+        _lib.check(_lib.load().lcbi_set_reserved_sms(n), "lcbi_set_reserved_sms")
+    try:
+        yield
+    finally:
+        if n:
+            _lib.load().lcbi_set_reserved_sms(0)
+
+
 class RingComm:
     """Double-buffered neighbour exchange: send tensors to rank+1 and receive from rank-1 on a side stream."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, reserved_sms=None):
+        self.reserved_sms = int(os.environ.get("LCBI_RING_RESERVED_SMS", 0)) if reserved_sms is None else int(reserved_sms)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -88,15 +110,16 @@ def ring_attention_forward(q, k, v, scale, comm, fwd_fn=_cuda_fwd, merge_fn=_cud
     k_nxt, v_nxt = (torch.empty_like(k_cur), torch.empty_like(v_cur)) if P > 1 else (None, None)
     acc = torch.empty(q.shape, dtype=torch.float32, device=q.device)
     lse = torch.empty((q.shape[0], q.shape[2], q.shape[1]), dtype=torch.float32, device=q.device)
-    for step in range(P):
-        if step + 1 < P:
-            comm.exchange([k_cur, v_cur], [k_nxt, v_nxt])
-        o_s, lse_s = fwd_fn(q, k_cur, v_cur, scale)
-        merge_fn(acc, lse, o_s, lse_s, step == 0)
-        if step + 1 < P:
-            comm.wait()
-            k_cur, k_nxt = k_nxt, k_cur
-            v_cur, v_nxt = v_nxt, v_cur
+    with _leave_sms_for_comm(comm, q.device):
+        for step in range(P):
+            if step + 1 < P:
+                comm.exchange([k_cur, v_cur], [k_nxt, v_nxt])
+            o_s, lse_s = fwd_fn(q, k_cur, v_cur, scale)
+            merge_fn(acc, lse, o_s, lse_s, step == 0)
+            if step + 1 < P:
+                comm.wait()
+                k_cur, k_nxt = k_nxt, k_cur
+                v_cur, v_nxt = v_nxt, v_cur
     return acc, lse
 
 
@@ -111,20 +134,21 @@ def ring_attention_backward(q, k, v, o, d_o, lse, scale, comm, bwd_fn=_cuda_bwd)
     if P > 1:
         k_nxt, v_nxt = torch.empty_like(k_cur), torch.empty_like(v_cur)
         dk_nxt, dv_nxt = torch.empty_like(dk_cur), torch.empty_like(dv_cur)
-    for step in range(P):
-        if step + 1 < P:
-            comm.exchange([k_cur, v_cur], [k_nxt, v_nxt])      # K/V prefetch overlaps this step's compute
-        bwd_fn(q, k_cur, v_cur, o, d_o, lse, scale, dq, dk_cur, dv_cur)
-        if P > 1:
+    with _leave_sms_for_comm(comm, q.device):
+        for step in range(P):
             if step + 1 < P:
+                comm.exchange([k_cur, v_cur], [k_nxt, v_nxt])      # K/V prefetch overlaps this step's compute
+            bwd_fn(q, k_cur, v_cur, o, d_o, lse, scale, dq, dk_cur, dv_cur)
+            if P > 1:
+                if step + 1 < P:
+                    comm.wait()
+                comm.exchange([dk_cur, dv_cur], [dk_nxt, dv_nxt])  # accumulators follow their shard (last hop: home)
                 comm.wait()
-            comm.exchange([dk_cur, dv_cur], [dk_nxt, dv_nxt])  # accumulators follow their shard (last hop: home)
-            comm.wait()
-            dk_cur, dk_nxt = dk_nxt, dk_cur
-            dv_cur, dv_nxt = dv_nxt, dv_cur
-            if step + 1 < P:
-                k_cur, k_nxt = k_nxt, k_cur
-                v_cur, v_nxt = v_nxt, v_cur
+                dk_cur, dk_nxt = dk_nxt, dk_cur
+                dv_cur, dv_nxt = dv_nxt, dv_cur
+                if step + 1 < P:
+                    k_cur, k_nxt = k_nxt, k_cur
+                    v_cur, v_nxt = v_nxt, v_cur
     return dq, dk_cur, dv_cur
 
 
