@@ -536,19 +536,18 @@ win_attn_bwd_dq_kernel(const WinParams p) {
   constexpr int kStride = Tile<D>::kStride;
   const int n_ks = n_pad / kKeySplit;
   const int nthreads = blockDim.x;
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + n_pad * kStride;
-  uint8_t* sQ = sV + n_pad * kStride;            // [32 rows]
-  uint8_t* sDO = sQ + kSlabRows * kStride;       // [32 rows]
-  float* tab = reinterpret_cast<float*>(sDO + kSlabRows * kStride);
-  float* s_lse = tab + round_up(g.tab_rows, 4);               // [32]
-  float* s_dsum = s_lse + kSlabRows;             // [32]
-  float* s_dq = s_dsum + kSlabRows;              // [n_ks][32][D] fp32 partial dQ
-  WinMeta meta;
-  meta.tok = reinterpret_cast<int*>(s_dq + n_ks * kSlabRows * D);
-  meta.reg = meta.tok + n_pad;
-  meta.row_term = meta.reg + n_pad;
-  meta.col_term = meta.row_term + n_pad;
+  // Per-window data is double-buffered: [K, V (n_pad rows), Q, dO (slab rows)] tiles and [tok, reg (n_pad), lse, dsum
+  // (slab)] metadata of the NEXT window are gathered with cp.async while the current window is processed.
+  const int tile_set_bytes = (2 * n_pad + 2 * kSlabRows) * kStride;
+  uint8_t* tiles = smem;                                          // [2][tile_set_bytes]
+  float* tab = reinterpret_cast<float*>(tiles + 2 * tile_set_bytes);
+  float* s_dq = tab + round_up(g.tab_rows, 4);                    // [n_ks][slab][D] fp32 partial dQ
+  int* s_rowterm = reinterpret_cast<int*>(s_dq + n_ks * kSlabRows * D);   // [n_pad] window-independent (bytes)
+  int* s_colterm = s_rowterm + n_pad;                             // [n_pad]
+  int* s_wmeta = s_colterm + n_pad;                               // [2][2 * n_pad + 2 * slab]: tok, reg, lse, dsum
+  const int wmeta_ints = 2 * n_pad + 2 * kSlabRows;
+  int* s_flags = s_wmeta + 2 * wmeta_ints;                        // [2]: bit 0 pad tokens present, bit 1 mask needed
+  const uint32_t tiles_base = static_cast<uint32_t>(__cvta_generic_to_shared(tiles));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qt = warp % QT, ks = warp / QT;
@@ -559,55 +558,129 @@ win_attn_bwd_dq_kernel(const WinParams p) {
   const float scale = p.scale_log2 / kLog2e;
 
   for (int t = tid; t < g.tab_rows; t += nthreads) tab[t] = p.table[t * p.H + h] * kLog2e;
+  for (int s0 = tid; s0 < n_pad; s0 += nthreads) {        // relative-position terms do not depend on the window
+    int rt = g.tab_rows - 1, ct = 0;                      // rt - ct stays a valid table row for dead slots
+    if (s0 < n) relpos_terms(g, s0, rt, ct);
+    s_rowterm[s0] = rt * 4;
+    s_colterm[s0] = ct * 4;
+  }
+  if (tid < 2) s_flags[tid] = 0;
 
   float dbias[16][4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) dbias[i][0] = dbias[i][1] = dbias[i][2] = dbias[i][3] = 0.f;
 
-  const uint32_t k_base = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
-  const uint32_t v_base = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
-  const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
-  const uint32_t do_base = static_cast<uint32_t>(__cvta_generic_to_shared(sDO));
   const int total_windows = p.win_count;
+  constexpr int kChunks = D / 8;
 
-  for (int wg = p.win_begin + split; wg < p.win_begin + total_windows; wg += p.win_splits) {
-    int b, w;
-  fdivmod(wg, g.d_nW, b, w);
-    __syncthreads();                              // previous window fully consumed
-    fill_meta(g, w, n_pad, meta, tid, nthreads);
-    __syncthreads();
-    const bool has_mask = window_has_mask(g, meta, tid, nthreads);
-    load_rows<D>(sK, p, meta.tok, b, h, 1, 0, n_pad, tid, nthreads);
-    load_rows<D>(sV, p, meta.tok, b, h, 2, 0, n_pad, tid, nthreads);
-    // slab rows: Q and dO (rows beyond n_pad cannot occur: row_base + 32 <= round_up(n, 32) <= n_pad)
-    {
-      constexpr int kChunks = D / 8;
-      for (int e = tid; e < kSlabRows * kChunks * 2; e += nthreads) {
-        const int which = e / (kSlabRows * kChunks);   // 0: Q, 1: dO
-        const int r = (e / kChunks) % kSlabRows, c = e % kChunks;
-        const int t = meta.tok[row_base + r];
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0) {
-          const __nv_bfloat16* src = which == 0
-              ? p.qkv + ((static_cast<int64_t>(b) * g.T + t) * 3) * p.C + h * D + c * 8
-              : p.d_out + (static_cast<int64_t>(b) * g.T + t) * p.C + h * D + c * 8;
-          val = *reinterpret_cast<const uint4*>(src);
-        }
-        *reinterpret_cast<uint4*>((which == 0 ? sQ : sDO) + r * kStride + c * 16) = val;
+  // slot -> token / region of window wg into metadata buffer `buf`; lse / dsum of the slab rows by 4-byte cp.async
+  auto window_meta = [&](int wg, int buf) {
+    int b, w, tok0, reg0;
+    fdivmod(wg, g.d_nW, b, w);
+    slot_lookup(g, w, 0, tok0, reg0);
+    int* wm = s_wmeta + buf * wmeta_ints;
+    int fl = 0;
+    for (int s0 = tid; s0 < n_pad; s0 += nthreads) {
+      int tok = -2, reg = -1;
+      if (s0 < n) {
+        slot_lookup(g, w, s0, tok, reg);
+        if (tok == -1) fl |= 1;
+        if (reg != reg0) fl |= 2;
       }
-      for (int r = tid; r < kSlabRows; r += nthreads) {
-        const int t = meta.tok[row_base + r];
-        float l = INFINITY, dsv = 0.f;
-        if (t >= 0) {
-          const int64_t idx = (static_cast<int64_t>(b) * g.T + t) * p.H + h;
-          l = p.lse2[idx];
-          dsv = p.dsum[idx];
+      wm[s0] = tok;
+      wm[n_pad + s0] = reg;
+      if (s0 >= row_base && s0 < row_base + kSlabRows) {
+        const int r = s0 - row_base;
+        float* lse_dst = reinterpret_cast<float*>(wm + 2 * n_pad) + r;
+        float* ds_dst = lse_dst + kSlabRows;
+        if (tok >= 0) {
+          const int64_t idx = (static_cast<int64_t>(b) * g.T + tok) * p.H + h;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(lse_dst))),
+                       "l"(p.lse2 + idx) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(ds_dst))),
+                       "l"(p.dsum + idx) : "memory");
+        } else {
+          *lse_dst = INFINITY;                      // pad / dead query rows: P = exp2(. - inf) = 0
+          *ds_dst = 0.f;
         }
-        s_lse[r] = l;
-        s_dsum[r] = dsv;
       }
     }
+    if (fl) atomicOr(&s_flags[buf], fl);
+  };
+  // cp.async of the window's K / V rows and the slab's Q / dO rows (zero fill for pad and dead rows)
+  auto issue_tiles = [&](int wg, int buf) {
+    int b, w;
+    fdivmod(wg, g.d_nW, b, w);
+    const int64_t tok_base = static_cast<int64_t>(b) * g.T;
+    const int* tk = s_wmeta + buf * wmeta_ints;
+    const uint32_t set_base = tiles_base + buf * tile_set_bytes;
+    const int total = (2 * n_pad + 2 * kSlabRows) * kChunks;
+    for (int e = tid; e < total; e += nthreads) {
+      const int row = e / kChunks, c = e % kChunks;        // row of the tile set: K rows, V rows, Q slab, dO slab
+      int slot, sel;
+      if (row < n_pad) { slot = row; sel = 1; }
+      else if (row < 2 * n_pad) { slot = row - n_pad; sel = 2; }
+      else if (row < 2 * n_pad + kSlabRows) { slot = row_base + row - 2 * n_pad; sel = 0; }
+      else { slot = row_base + row - 2 * n_pad - kSlabRows; sel = 3; }
+      const int t = tk[slot];
+      const __nv_bfloat16* src = p.qkv;                    // any valid address when nothing is read (zero fill)
+      if (t >= 0)
+        src = sel < 3 ? p.qkv + ((tok_base + t) * 3 + sel) * p.C + h * D + c * 8
+                      : p.d_out + (tok_base + t) * p.C + h * D + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(set_base + row * kStride + c * 16), "l"(src),
+                   "r"(t >= 0 ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int wg_first = p.win_begin + split;
+  const int wg_end = p.win_begin + total_windows;
+  __syncthreads();                                  // table, terms and flags written
+  if (wg_first < wg_end) {
+    window_meta(wg_first, 0);
     __syncthreads();
+    issue_tiles(wg_first, 0);
+  }
+
+  int it = 0;
+  for (int wg = wg_first; wg < wg_end; wg += p.win_splits, ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    const int wg_next = wg + p.win_splits;
+    int b, w;
+    fdivmod(wg, g.d_nW, b, w);
+    const int* m_tok = s_wmeta + cur * wmeta_ints;
+    const int* m_reg = m_tok + n_pad;
+    const float* s_lse = reinterpret_cast<const float*>(m_tok + 2 * n_pad);
+    const float* s_dsum = s_lse + kSlabRows;
+    uint8_t* sK = tiles + cur * tile_set_bytes;
+    const uint32_t k_base = tiles_base + cur * tile_set_bytes, v_base = k_base + n_pad * kStride;
+    const uint32_t q_base = v_base + n_pad * kStride, do_base = q_base + kSlabRows * kStride;
+
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int flags = s_flags[cur];
+    if ((flags & 1) && p.qkv_bias != nullptr) {
+      // pad tokens enter the reference as zeros before the qkv Linear, so their k / v rows are the Linear's bias
+      for (int e = tid; e < 2 * n_pad * kChunks; e += nthreads) {
+        const int row = e / kChunks, c = e % kChunks;
+        const int slot = row < n_pad ? row : row - n_pad, sel = row < n_pad ? 1 : 2;
+        if (m_tok[slot] != -1) continue;
+        const float* bsrc = p.qkv_bias + sel * p.C + h * D + c * 8;
+        uint4 val;
+        val.x = pack2_bf16(bsrc[0], bsrc[1]);
+        val.y = pack2_bf16(bsrc[2], bsrc[3]);
+        val.z = pack2_bf16(bsrc[4], bsrc[5]);
+        val.w = pack2_bf16(bsrc[6], bsrc[7]);
+        *reinterpret_cast<uint4*>(sK + row * kStride + c * 16) = val;
+      }
+    }
+    if (tid == 0) s_flags[nxt] = 0;                 // (last read one iteration ago; set again after the barrier)
+    __syncthreads();                                // this window's data is in; the previous window is fully consumed
+    if (wg_next < wg_end) {
+      window_meta(wg_next, nxt);
+      __syncthreads();
+      issue_tiles(wg_next, nxt);                    // lands while this window is processed
+    }
+    const bool has_mask = (flags & 2) != 0;
 
     uint32_t aq[D / 16][4], ado[D / 16][4];
 #pragma unroll
@@ -619,8 +692,8 @@ win_attn_bwd_dq_kernel(const WinParams p) {
     const int i0 = row_base + r0, i1 = row_base + r1;         // window slots
     const float lse0 = s_lse[r0], lse1 = s_lse[r1], ds0 = s_dsum[r0], ds1 = s_dsum[r1];
     const uint32_t tab_base = static_cast<uint32_t>(__cvta_generic_to_shared(tab));
-    const uint32_t tb0 = tab_base + meta.row_term[i0], tb1 = tab_base + meta.row_term[i1];
-    const int rg0 = meta.reg[i0], rg1 = meta.reg[i1];
+    const uint32_t tb0 = tab_base + s_rowterm[i0], tb1 = tab_base + s_rowterm[i1];
+    const int rg0 = m_reg[i0], rg1 = m_reg[i1];
     float dq[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -650,9 +723,9 @@ win_attn_bwd_dq_kernel(const WinParams p) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int j = key0 + nt * 8 + qq * 2;
-          const int2 ct = *reinterpret_cast<const int2*>(meta.col_term + j);
+          const int2 ct = *reinterpret_cast<const int2*>(s_colterm + j);
           int2 rj = make_int2(0, 0);
-          if (kMasked) rj = *reinterpret_cast<const int2*>(meta.reg + j);
+          if (kMasked) rj = *reinterpret_cast<const int2*>(m_reg + j);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int cte = e ? ct.y : ct.x;
@@ -698,7 +771,7 @@ win_attn_bwd_dq_kernel(const WinParams p) {
     __syncthreads();
     for (int e = tid; e < kSlabRows * (D / 8); e += nthreads) {
       const int r = e / (D / 8), c = e % (D / 8);
-      const int t = meta.tok[row_base + r];
+      const int t = m_tok[row_base + r];
       if (t < 0) continue;
       float acc[8] = {};
       for (int s2 = 0; s2 < n_ks; ++s2) {
@@ -740,9 +813,9 @@ win_attn_bwd_dq_kernel(const WinParams p) {
 size_t dq_smem_bytes(const WinGeom& g, int D, int slab_rows) {
   const int n_pad = round_up(g.n, kKeySplit);
   const int n_ks = n_pad / kKeySplit;
-  return static_cast<size_t>(2) * n_pad * (D * 2 + 16) + static_cast<size_t>(2) * slab_rows * (D * 2 + 16) +
-         static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 + 2 * slab_rows * 4 + static_cast<size_t>(n_ks) * slab_rows * D * 4 +
-         static_cast<size_t>(n_pad) * 16;
+  const size_t tile_set = static_cast<size_t>(2 * n_pad + 2 * slab_rows) * (D * 2 + 16);
+  return 2 * tile_set + static_cast<size_t>(round_up(g.tab_rows, 4)) * 4 + static_cast<size_t>(n_ks) * slab_rows * D * 4 +
+         static_cast<size_t>(2) * n_pad * 4 + static_cast<size_t>(2) * (2 * n_pad + 2 * slab_rows) * 4 + 16;
 }
 
 template <typename K>
