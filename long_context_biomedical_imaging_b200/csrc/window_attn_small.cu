@@ -13,6 +13,8 @@
 //     ids); interior windows skip it;
 //   * K and V fragments are loaded to registers once per window and reused by the four 16-row query tiles.
 #include "lcbi_kernels.h"
+#include <type_traits>
+
 #include "window_common.cuh"
 
 namespace lcbi {
@@ -350,12 +352,17 @@ win_attn_bwd_small_kernel(const WinParams p) {
   // ---- per-window gather pipeline -----------------------------------------------------------------------------
   // window_meta: slot -> token / region (closed form) and the token's lse / dsum, for one window, by threads 0-63;
   // issue_tiles: cp.async of the window's q / k / v / dO rows (zero-fill for pad and dead rows).
-  struct MetaRegs { int tok, reg; float lse, dsum; };
+  struct MetaRegs { int tok, reg; float lse, dsum; bool mixed = false; };
   auto window_meta = [&](int u) {
     MetaRegs m{-2, -1, INFINITY, 0.f};              // pad / dead query rows: P = exp2(. - inf) = 0
     int b, w;
     fdivmod(p.win_begin + u, g.d_nW, b, w);
     if (tid < n) slot_lookup(g, w, tid, m.tok, m.reg);
+    {
+      int tok0, reg0;
+      slot_lookup(g, w, 0, tok0, reg0);
+      m.mixed = tid < n && m.reg != reg0;           // the window straddles a shift-mask region boundary
+    }
     if (m.tok >= 0) {
       const int64_t idx = (static_cast<int64_t>(b) * g.T + m.tok) * p.H + h;
       m.lse = __ldg(p.lse2 + idx);
@@ -370,7 +377,8 @@ win_attn_bwd_small_kernel(const WinParams p) {
     reinterpret_cast<int*>(mb)[128 + tid] = m.tok;
     reinterpret_cast<int*>(mb)[192 + tid] = m.reg;
     const unsigned pads = __ballot_sync(0xffffffffu, m.tok == -1);
-    if (lane == 0 && pads) atomicOr(&s_pad[buf], 1);
+    const unsigned mixed = __ballot_sync(0xffffffffu, m.mixed);
+    if (lane == 0 && (pads | mixed)) atomicOr(&s_pad[buf], (pads ? 1 : 0) | (mixed ? 2 : 0));
   };
   auto issue_tiles = [&](int u, int buf) {
     int b, w;
@@ -415,7 +423,8 @@ win_attn_bwd_small_kernel(const WinParams p) {
     const uint32_t v_base = k_base + L::kTileBytes, do_base = v_base + L::kTileBytes;
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (s_pad[cur] && p.qkv_bias != nullptr) {
+    const int flags = s_pad[cur];
+    if ((flags & 1) && p.qkv_bias != nullptr) {
       // pad tokens enter the reference as zeros before the qkv Linear, so their q / k / v rows are the Linear's bias
       for (int e = tid; e < 3 * 64 * kChunks; e += 128) {
         const int sel = e / (64 * kChunks), r = (e / kChunks) & 63, c = e % kChunks;
@@ -465,31 +474,42 @@ win_attn_bwd_small_kernel(const WinParams p) {
             mma_bf16_16816(dp[nt], ado[kk], b0, b1);
           }
         }
+        auto probs = [&](auto masked_c) {
+          constexpr bool kMasked = decltype(masked_c)::value;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          float pv[4];
+          for (int nt = 0; nt < 4; ++nt) {
+            const int j = half * 32 + nt * 8 + qq * 2;
+            const int2 ct = *reinterpret_cast<const int2*>(s_ct + j);     // dead columns: col_term 0 (valid gather)
+            int2 rj = make_int2(0, 0);
+            if (kMasked) rj = *reinterpret_cast<const int2*>(s_reg + j);
+            float pv[4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = half * 32 + nt * 8 + qq * 2 + e;
-            float p0 = 0.f, p1 = 0.f;
-            if (j < n) {
-              const int ct = s_ct[j], rj = s_reg[j];
-              p0 = ex2f(fmaf(s[nt][e], p.scale_log2, tab[rt0 - ct]) + (rg0 != rj ? mask_log2 : 0.f) - lse0);
-              p1 = ex2f(fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - ct]) + (rg1 != rj ? mask_log2 : 0.f) - lse1);
+            for (int e = 0; e < 2; ++e) {
+              const int cte = e ? ct.y : ct.x;
+              float l0 = fmaf(s[nt][e], p.scale_log2, tab[rt0 - cte]) - lse0;
+              float l1 = fmaf(s[nt][2 + e], p.scale_log2, tab[rt1 - cte]) - lse1;
+              if (kMasked) {
+                const int rje = e ? rj.y : rj.x;
+                l0 += rg0 != rje ? mask_log2 : 0.f;
+                l1 += rg1 != rje ? mask_log2 : 0.f;
+              }
+              const bool live = j + e < n;          // dead key columns must not reach dBias / dK / dV
+              const float p0 = live ? ex2f(l0) : 0.f, p1 = live ? ex2f(l1) : 0.f;
+              pv[e] = p0;
+              pv[2 + e] = p1;
+              dp[nt][e] = p0 * (dp[nt][e] - ds0);
+              dp[nt][2 + e] = p1 * (dp[nt][2 + e] - ds1);
+              dbias[half * 4 + nt][e] += dp[nt][e];
+              dbias[half * 4 + nt][2 + e] += dp[nt][2 + e];
             }
-            pv[e] = p0;
-            pv[2 + e] = p1;
-            dp[nt][e] = p0 * (dp[nt][e] - ds0);
-            dp[nt][2 + e] = p1 * (dp[nt][2 + e] - ds1);
-            dbias[half * 4 + nt][e] += dp[nt][e];
-            dbias[half * 4 + nt][2 + e] += dp[nt][2 + e];
+            const int col = j * 2;
+            *reinterpret_cast<uint32_t*>(sP + i0 * kPStride + col) = pack2_bf16(pv[0], pv[1]);
+            *reinterpret_cast<uint32_t*>(sP + i1 * kPStride + col) = pack2_bf16(pv[2], pv[3]);
+            *reinterpret_cast<uint32_t*>(sDS + i0 * kPStride + col) = pack2_bf16(dp[nt][0], dp[nt][1]);
+            *reinterpret_cast<uint32_t*>(sDS + i1 * kPStride + col) = pack2_bf16(dp[nt][2], dp[nt][3]);
           }
-          const int col = (half * 32 + nt * 8 + qq * 2) * 2;
-          *reinterpret_cast<uint32_t*>(sP + i0 * kPStride + col) = pack2_bf16(pv[0], pv[1]);
-          *reinterpret_cast<uint32_t*>(sP + i1 * kPStride + col) = pack2_bf16(pv[2], pv[3]);
-          *reinterpret_cast<uint32_t*>(sDS + i0 * kPStride + col) = pack2_bf16(dp[nt][0], dp[nt][1]);
-          *reinterpret_cast<uint32_t*>(sDS + i1 * kPStride + col) = pack2_bf16(dp[nt][2], dp[nt][3]);
-        }
+        };
+        if (flags & 2) probs(std::true_type{}); else probs(std::false_type{});
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           uint32_t ads[4];
