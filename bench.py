@@ -309,8 +309,8 @@ def run_swin(args, dist, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of dense_attn_bwd_kernel at 16 volumes (276.9 MB + 127.1 MB), per volume
-BWD_DRAM_BYTES_PER_VOLUME = (276_902_400 + 127_062_784) // 16
+# dram__bytes_read.sum + dram__bytes_write.sum of dense_attn_bwd_kernel at 16 volumes (265.9 MB + 125.7 MB), per volume
+BWD_DRAM_BYTES_PER_VOLUME = (265_883_904 + 125_711_872) // 16
 
 
 def main():
@@ -482,7 +482,7 @@ def main():
                          "achieved": bwd_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": bwd_tflops / peaks["bf16_tflops"], "traffic": BWD_DRAM_BYTES_PER_VOLUME * B,
                          "traffic_unit": "bytes per launch (dram read + write of dense_attn_bwd_kernel, one ncu --set full "
-                                         "capture at 16 volumes: profiles/r01_ncu_dense_v4_summary.csv, scaled by volumes)",
+                                         "capture at 16 volumes: profiles/r01_ncu_dense_final_summary.csv, scaled by volumes)",
                          "peak_source": peaks["source"] + " (burst)", "peak_sustained": peaks["bf16_tflops_sustained"],
                          "algorithmic_flops_per_launch": bwd_flops, "avg_launch_ms": bwd_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
