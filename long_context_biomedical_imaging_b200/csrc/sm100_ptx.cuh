@@ -36,15 +36,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Same packing on the integer pipe: round half away from zero by adding half a bf16 ulp to the bit pattern, then a
-// byte permute picks the two upper halves. F2FP (cvt.rn.bf16x2.f32) issues on the same quarter-rate XU pipe as
-// MUFU.EX2 on sm_100 (ncu: sm__inst_executed_pipe_xu counts both), so in the exp-bound attention loops the
-// conversions would cost as much as the exponentials; IADD + PRMT run on the ALU pipe instead. Differs from
-// round-to-nearest-even only on exact ties; finite inputs only.
-__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
-  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   // cvt.rn.bf16x2.f32 d, a, b : d.hi = a, d.lo = b
