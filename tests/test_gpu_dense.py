@@ -257,3 +257,29 @@ def test_dense_full_size_properties():
     o_b, lse_b = ops.dense_attn_fwd(q, k[:, perm].contiguous(), v[:, perm].contiguous(), 0.125)
     assert max_rel(o_b.float().cpu(), o_a.float().cpu()) < 1e-2
     assert max_rel(lse_b.cpu(), lse_a.cpu()) < 1e-5
+
+
+def test_dense_backward_full_size_properties():
+    """cfg3 at the bench size (B=16): size-independent identities of the attention gradient.
+    (1) with every value row equal, O does not depend on the scores, so dQ = dK = 0;
+    (2) rows of P sum to one, so sum_keys dV[key, :] = sum_queries dO[query, :]."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(5)
+    B, N, H, d = 16, 1728, 12, 64
+    q, k, v = [torch.randn(B, N, H, d, device="cuda").to(torch.bfloat16) for _ in range(3)]
+    d_o = torch.randn(B, N, H, d, device="cuda").to(torch.bfloat16)
+    o, lse = ops.dense_attn_fwd(q, k, v, 0.125)
+    dq, dk, dv = ops.dense_attn_bwd(q, k, v, o, d_o, lse, 0.125)
+    want = d_o.float().sum(dim=1)                       # (B, H, d)
+    got = dv.float().sum(dim=1)
+    assert max_rel(got.cpu(), want.cpu()) < 1e-2
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all()
+
+    v_same = torch.randn(B, 1, H, d, device="cuda").to(torch.bfloat16).expand(B, N, H, d).contiguous()
+    o2, lse2 = ops.dense_attn_fwd(q, k, v_same, 0.125)
+    assert max_rel(o2.float().cpu(), v_same.float().cpu()) < 1e-2
+    dq2, dk2, _ = ops.dense_attn_bwd(q, k, v_same, o2, d_o, lse2, 0.125)
+    scale_ref = float(dq.float().abs().max())            # gradient magnitude of the generic case
+    assert float(dq2.float().abs().max()) < 2e-2 * scale_ref
+    assert float(dk2.float().abs().max()) < 2e-2 * float(dk.float().abs().max())

@@ -233,3 +233,42 @@ def test_window_ranges_partition_the_block(case):
     assert torch.equal(g_sum[0].to(torch.bfloat16), g_full[0])           # dqkv rows are disjoint too
     assert max_rel(g_sum[1].cpu(), g_full[1].float().cpu()) < 1e-3      # fp32 atomics: order differs
     assert max_rel(g_sum[2].cpu(), g_full[2].float().cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=16, grid=(128, 128), window=(7, 7), C=96, heads=3),          # cfg2 stage 1, bench size
+    dict(B=1, grid=(64, 64, 64), window=(7, 7, 7), C=48, heads=3),      # cfg4 stage 1 ('unetr'): 1000 windows of 343
+])
+def test_window_attention_full_size_properties(case):
+    """BASELINE full sizes, no n^2 oracle: when every value row (including the pad tokens' bias row) is the same
+    vector, each softmax row sums to one and the output equals that vector at every token whatever the bias table and
+    the shift mask do; consequently d(q), d(k) and d(table) vanish and d(v) sums to sum(dO) per window set."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(9)
+    B, grid, heads, C = case["B"], case["grid"], case["heads"], case["C"]
+    window = case["window"]
+    shift = tuple(w // 2 for w in window)
+    qkv = (torch.randn(B, *grid, 3 * C, device="cuda") * 0.7).to(torch.bfloat16)
+    vrow = torch.randn(C, device="cuda").to(torch.bfloat16)
+    qkv[..., 2 * C:] = vrow
+    qkv.requires_grad_(True)
+    bias = torch.randn(3 * C, device="cuda")
+    bias[2 * C:] = vrow.float()
+    bias.requires_grad_(True)
+    n_tab = 1
+    for w in window:
+        n_tab *= 2 * w - 1
+    table = (torch.randn(n_tab, heads, device="cuda") * 0.5).requires_grad_(True)
+    out = ops.window_attention(qkv, bias, table, grid, window, shift, heads)
+    assert max_rel(out.detach().float().cpu(), vrow.float().expand_as(out).cpu()) < 1e-2
+    d_out = torch.randn_like(out)
+    out.backward(d_out)
+    g = qkv.grad.float()
+    ref_mag = float(g[..., 2 * C:].abs().max())          # dv carries the whole gradient
+    assert float(g[..., :2 * C].abs().max()) < 2e-2 * ref_mag
+    assert float(table.grad.abs().max()) < 2e-2 * ref_mag * 50
+    # sum over tokens of dv (+ the pad tokens' share in d(bias_v)) = sum over tokens of dO
+    total_dv = g[..., 2 * C:].sum(dim=tuple(range(len(grid) + 1))) + bias.grad[2 * C:]
+    total_do = d_out.float().sum(dim=tuple(range(len(grid) + 1)))
+    assert max_rel(total_dv.cpu(), total_do.cpu()) < 2e-2
