@@ -42,10 +42,9 @@ def _cuda_merge(acc, lse_acc, o_s, lse_s, first):
 @contextlib.contextmanager
 def _leave_sms_for_comm(comm, device):
     """The dense kernels are persistent (they hold every SM for a whole launch), so the NCCL send/recv kernels of the
-    side stream may only start once a launch retires. While a ring pass runs, the kernels can leave
-    `comm.reserved_sms` SMs unused (`lcbi_set_reserved_sms`; env LCBI_RING_RESERVED_SMS). Default 0: at 2 GPUs the
-    exchange is small next to a step's compute and giving up SMs only cost time (459.8 ms with 0, 474.1 with 8,
-    490.7 with 16 reserved SMs per cfg5 step)."""
+    side stream may only start once a launch retires and the exchange does not overlap the compute. While a ring
+    pass runs, the kernels leave `comm.reserved_sms` SMs unused (`lcbi_set_reserved_sms`; env
+    LCBI_RING_RESERVED_SMS; the default depends on the ring size, see RingComm)."""
     n = comm.reserved_sms if (comm.world > 1 and device.type == "cuda") else 0
     if n:
         from . import _lib
@@ -61,8 +60,14 @@ class RingComm:
     """Double-buffered neighbour exchange: send tensors to rank+1 and receive from rank-1 on a side stream."""
 
     def __init__(self, group=None, reserved_sms=None):
-        self.reserved_sms = int(os.environ.get("LCBI_RING_RESERVED_SMS", 0)) if reserved_sms is None else int(reserved_sms)
         self.group = group
+        world = dist.get_world_size(group)
+        if reserved_sms is None:
+            # measured at cfg5: 8 ranks 134.0 ms with 0, 122.7 ms with 8, 128.7 ms with 16 reserved SMs;
+            # 2 ranks 459.8 / 474.1 / 490.7 ms (the exchange is small next to a step's compute there)
+            default = 8 if world >= 8 else (4 if world >= 4 else 0)
+            reserved_sms = int(os.environ.get("LCBI_RING_RESERVED_SMS", default))
+        self.reserved_sms = int(reserved_sms)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.send_to = dist.get_global_rank(group, (self.rank + 1) % self.world) if group is not None else (self.rank + 1) % self.world
