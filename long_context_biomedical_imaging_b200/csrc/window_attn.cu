@@ -15,10 +15,9 @@
 // work per (window, head) is far below a tcgen05 tile; the bound is HBM traffic / exp throughput, not the
 // tensor pipe ("window attention roofline").
 #include <cstdlib>
-
-#include "lcbi_kernels.h"
 #include <type_traits>
 
+#include "lcbi_kernels.h"
 #include "window_common.cuh"
 
 #ifndef LCBI_WIN_NT

@@ -1,20 +1,19 @@
-// Swin window attention forward for SMALL windows (<= 64 tokens: 7x7, 8x8, 4x4x4, clamped windows).
+// Swin window attention for SMALL windows (<= 64 tokens: 7x7, 8x8, 4x4x4, clamped windows), forward and backward.
 //
-// Same operation as win_attn_fwd_kernel (window_attn.cu) — the reference's forward_part1 gather / attention core
-// / scatter, /root/reference/model/models/backbone_swin.py:339-357, :441-485, :591-628 — but organised for the
-// regime where a whole (window, head) fits one warp and the per-element bias / mask bookkeeping, not the MMAs,
-// dominates the instruction count:
-//   * persistent CTAs, one per (head, slice of the window list): 8 warps, each warp owns one (window, head) at a
-//     time — no block-level synchronisation inside the loop, the warps' load and compute phases interleave;
-//   * the relative-position bias of the head is expanded ONCE per CTA into a 64 x 64 fp32 shared-memory tile
-//     (already multiplied by log2 e, -inf in the columns beyond the window), so the inner loop adds it with one
-//     conflict-free 8-byte load per two logits instead of re-deriving table indices;
-//   * the shift-mask test runs only for windows that actually straddle a shift boundary (warp vote on the region
-//     ids); interior windows skip it;
-//   * K and V fragments are loaded to registers once per window and reused by the four 16-row query tiles.
-#include "lcbi_kernels.h"
+// Same operation as the kernels of window_attn.cu — the reference's forward_part1 gather / attention core / scatter,
+// /root/reference/model/models/backbone_swin.py:339-357, :441-485, :591-628 — organised for the regime where a whole
+// (window, head) is one 64 x 64 tile and the gather latency and the per-element bias / mask bookkeeping, not the
+// MMAs, dominate:
+//   * persistent CTAs, one per (head, slice of the window list), 4 warps = the four 16-row tiles of a window;
+//   * the rows and the slot -> token map of the NEXT window are gathered with cp.async into a second buffer while the
+//     current window is processed;
+//   * forward: the head's relative-position bias tile is held in registers for the whole kernel (x log2 e, -inf in
+//     the key columns beyond the window), so a logit costs one FFMA;
+//   * the shift-mask test runs only for windows that straddle a shift boundary (flag computed with the slot map);
+//   * backward: one fused kernel for dq, dk, dv, d(qkv.bias) and d(bias table) (see below).
 #include <type_traits>
 
+#include "lcbi_kernels.h"
 #include "window_common.cuh"
 
 namespace lcbi {
