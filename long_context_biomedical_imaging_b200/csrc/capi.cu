@@ -37,6 +37,33 @@ using namespace lcbi;
 static int g_reserved_sms = 0;
 namespace lcbi {
 int reserved_sms() { return g_reserved_sms; }
+
+bool first_launch_on_current_device(unsigned long long* seen_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown: configure every time
+  const unsigned long long bit = 1ull << dev;
+  const unsigned long long old = __atomic_fetch_or(seen_mask, bit, __ATOMIC_RELAXED);
+  return (old & bit) == 0;
+}
+
+int current_device_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_cuda_error(e);
+    return 0;
+  }
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) {
+    set_cuda_error(e);
+    return 0;
+  }
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
 }  // namespace lcbi
 
 extern "C" {

@@ -47,7 +47,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 constexpr int kStep = 64;                          // queries per pipeline step
 constexpr int kStepBytes = kStep * kHeadDim * 2;   // 8 KB
-constexpr int kQStages = 4;
+#ifndef LCBI_BWD_QSTAGES
+#define LCBI_BWD_QSTAGES 4
+#endif
+constexpr int kQStages = LCBI_BWD_QSTAGES;   // ring depth of the Q / dO / row-term step tiles
 // Per-query row terms ride along as one extra K=16 step of the S^T / dP^T GEMMs: the fp32 value is split into three
 // bf16 parts (hi, mid, lo) stored in columns 0-2 of a [64 queries x 16] K-major tile, multiplied by a constant
 // [128 keys x 16] tile holding (1, 1, 1, 0, ...). Tiles use the un-swizzled canonical layout: 8-row x 16-byte core
@@ -63,7 +66,36 @@ __host__ __device__ constexpr int aug_chunk_offset(int row) {   // byte offset o
 // place, the first half of the columns their owner thread read (thread (row, hh) owns columns [32hh, 32hh+32) of a
 // buffer and writes 16 packed columns at [32hh, 32hh+16)); K and V sit in TMEM as the A operands of S^T / dP^T.
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemK = 448, kTmemV = 480;
-   // dQ partials: red.global.add.v4.f32 from registers (no smem staging)
+
+// 1: the drain warps add dQ partials to the fp32 accumulator with red.global from registers; 0: through a swizzled
+// fp32 staging tile and TMA reduce-adds
+#ifndef LCBI_BWD_DQ_RED
+#define LCBI_BWD_DQ_RED 0
+#endif
+
+// 2^x on the FMA / integer pipes: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial of
+// 2^f (relative error 7.5e-5, far below the bf16 rounding P^T gets anyway), n added to the exponent field.
+// 1: warps 0-3 process the even 64-query steps and warps 4-7 the odd ones (all 64 columns each); 0: every compute warp
+// works on every step, warps 0-3 on query columns 0-31 and warps 4-7 on columns 32-63
+#ifndef LCBI_BWD_SPLIT_STEPS
+#define LCBI_BWD_SPLIT_STEPS 0
+#endif
+// 1: the compute warps process their 32 columns in four chunks of 8 inside a rolled loop (see the loop)
+#ifndef LCBI_BWD_CHUNKED
+#define LCBI_BWD_CHUNKED 0
+#endif
+#ifndef LCBI_BWD_POLY_EXP
+#define LCBI_BWD_POLY_EXP 0
+#endif
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;             // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float r = fmaf(f, 0.0551716648f, 0.2426111251f);
+  r = fmaf(f, r, 0.6932609677f);
+  r = fmaf(f, r, 0.9999280572f);
+  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
+}
 
 struct __align__(1024) BwdSmem {
   uint8_t k[2][kTileBytes];             // K of item it in k[it & 1]: the next item's K is prefetched during this one
@@ -71,7 +103,7 @@ struct __align__(1024) BwdSmem {
   uint8_t q[kQStages][kStepBytes];      // 64-query tiles; together also the dK staging area of the epilogue
   uint8_t dout[kQStages][kStepBytes];   // likewise dV staging
   uint8_t ds[2][2 * kTileBytes];        // dS^T per 128-query tile (double-buffered): two [128 keys x 64 queries] atoms
-  uint8_t dq_stage[2 * kTileBytes];     // two [128 queries x 32 fp32] SW128 tiles
+  uint8_t dq_stage[LCBI_BWD_DQ_RED ? 1024 : 2 * kTileBytes];   // two [128 queries x 32 fp32] SW128 tiles (TMA-reduce drain)
   uint8_t lse_aug[kQStages][kAugBytes];   // per-query -lse/scale as the B operand of one extra k-step of S^T
   uint8_t d_aug[kQStages][kAugBytes];     // per-query -D likewise for dP^T
   uint8_t ones[2 * kAugBytes];            // [128 keys x 8] constant A operand of those k-steps: (1, 1, 1, 0, ...)
@@ -106,6 +138,8 @@ __device__ __forceinline__ long long global_ns() {
 #define LCBI_TR(role, step, ev) do { } while (0)
 #define LCBI_ITEM_T(slot) do { } while (0)
 #endif
+
+static_assert(sizeof(BwdSmem) + 1024 <= 232448, "BwdSmem exceeds the 227 KB dynamic shared memory limit");
 
 struct BwdParams {
   int B, H, Nq, Nk, Nq_pad;
@@ -273,7 +307,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.sdp_full[b], 1);
-      mbar_init(&sm.pds_full[b], 8);   // one arrive per compute warp
+      mbar_init(&sm.pds_full[b], LCBI_BWD_SPLIT_STEPS ? 4 : 8);   // one arrive per compute warp working on the buffer
     }
     mbar_init(&sm.kvt_full, 8);
     mbar_init(&sm.dq_full, 1);
@@ -457,6 +491,60 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mbar_wait(&sm.dq_full, gi & 1);
         if (issuer && it == 0) LCBI_TR(3, i, 0);
         tc_fence_after();
+#if LCBI_BWD_DQ_RED
+        // dQ partials go from registers straight into the fp32 accumulator: with the 16x256b fragment layout a quad
+        // of threads owns 32 contiguous bytes of one query row, so every red.v2 quad fills one whole L2 sector
+        // (no staging tile, no TMA reduce, no barriers among the drain warps).
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_16x256b_x8(t_dq, ra);                  // query rows  0-15 of this warp's 32
+          tmem_ld_16x256b_x8(t_dq + (16u << 16), rb);    // query rows 16-31
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.dq_empty);
+          const int q0 = i * kTile + (warp & 3) * 32 + (lane >> 2);
+          float* const col0 = p.dq_acc + (static_cast<size_t>(batch) * p.Nq * p.H + head) * kHeadDim + (lane & 3) * 2;
+#if LCBI_BWD_DQ_RED == 2
+          // neighbours in a quad swap pairs, so that the even thread owns four contiguous columns of row g and the odd
+          // thread the same four columns of row g + 8: half as many (16-byte) reds, two of them fill a sector
+          const bool odd = lane & 1;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t* r = half ? rb : ra;
+            const int q = q0 + half * 16 + (odd ? 8 : 0);
+            float* dst = col0 - (odd ? 2 : 0) + static_cast<size_t>(q) * p.H * kHeadDim;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // even keeps (r0, r1) of row g and receives the odd neighbour's (r0, r1); odd keeps (r2, r3) of row g + 8
+              // and receives the even neighbour's (r2, r3)
+              const uint32_t s0 = odd ? r[4 * j] : r[4 * j + 2], s1 = odd ? r[4 * j + 1] : r[4 * j + 3];
+              const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+              const float a0 = __uint_as_float(odd ? x0 : r[4 * j]), a1 = __uint_as_float(odd ? x1 : r[4 * j + 1]);
+              const float a2 = __uint_as_float(odd ? r[4 * j + 2] : x0), a3 = __uint_as_float(odd ? r[4 * j + 3] : x1);
+              if (q < p.Nq) red_add_f32x4(dst + j * 8, a0 * p.scale, a1 * p.scale, a2 * p.scale, a3 * p.scale);
+            }
+          }
+#else
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t* r = half ? rb : ra;
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const int q = q0 + half * 16 + v * 8;
+              if (q < p.Nq) {
+                float* dst = col0 + static_cast<size_t>(q) * p.H * kHeadDim;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  red_add_f32x2(dst + j * 8, __uint_as_float(r[4 * j + 2 * v]) * p.scale,
+                                __uint_as_float(r[4 * j + 2 * v + 1]) * p.scale);
+              }
+            }
+          }
+#endif
+          if (issuer && it == 0) LCBI_TR(3, i, 1);
+        }
+#else
         uint32_t r[64];
         tmem_ld_x32(t_dq, r);
         tmem_ld_x32(t_dq + 32, r + 32);
@@ -482,9 +570,11 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tma_store_commit();
         }
         if (issuer && it == 0) LCBI_TR(3, i, 1);
+#endif
       }
     }
     if (issuer) tma_store_wait_read<0>();
+    (void)row;
   } else if (warp < 8) {
     // ------------------------------------------------------------------ P^T and dS^T in one pass (warps 0-7)
     const int hh = warp >> 2;                   // which 32-query half of the 64-query step this thread handles
@@ -495,6 +585,10 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     bool store_pending = false;                 // the previous item's dV/dK store may still be reading its staging tiles
     auto finish_store = [&]() {
       if (store_issuer) tma_store_wait_read<0>();
+#if LCBI_BWD_SPLIT_STEPS
+      if (!p.accumulate_dkv) named_bar_sync(5 + hh, 128);   // the staging atom is this group's own
+      else
+#endif
       named_bar_sync(7, 256);
       store_pending = false;
     };
@@ -527,6 +621,51 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       LCBI_ITEM_T(0);
       if (it == 0) copy_kv_to_tmem(0);           // later items: done at the end of the previous item's last step
 
+#if LCBI_BWD_SPLIT_STEPS
+      // Warps 0-3 take the even steps, warps 4-7 the odd ones, each all 64 query columns of its step (two passes of 32).
+      // A group then always works on the same S^T / dP^T buffer (b == hh), and the two warps that share an SM
+      // sub-partition run half a step apart: one is in its MUFU burst while the other packs, stores and fences.
+      for (int s = hh; s < n_steps; s += 2) {
+        const int gs = gs0 + s, b = gs & 1, gi = gi0 + (s >> 1);
+        // staging tile of this group's previous dV / dK store = the dS^T atom this group writes at step 2 + hh
+        // (fp32 accumulate mode: both buffers, so both groups meet at their first step)
+        if (store_pending && (p.accumulate_dkv || s == 2 + hh)) finish_store();
+        mbar_wait(&sm.sdp_full[b], (gs >> 1) & 1);
+        tc_fence_after();
+        uint8_t* ds_atom = sm.ds[gi & 1] + (s & 1) * kTileBytes;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sv[32], dpv[32];
+          tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + half * 32, sv);
+          tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + half * 32, dpv);
+          tmem_ld_wait();
+          uint32_t pk[16], dsk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, half * 4 + g))),
+                         "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
+          tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + half * 32, pk);
+          tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + half * 32, dsk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.pds_full[b]);
+      }
+      // the other group's last S^T / dP^T GEMMs must have retired too before K / V of the next item replace this
+      // item's in TMEM (that barrier cannot complete another phase before this thread has copied its rows)
+      {
+        const int s_other = n_steps - 1 - hh;     // last step of the other parity
+        mbar_wait(&sm.sdp_full[s_other & 1], ((gs0 + s_other) >> 1) & 1);
+      }
+#else
       for (int s = 0; s < n_steps; ++s) {
         const int gs = gs0 + s, b = gs & 1, gi = gi0 + (s >> 1);
         // the staging tiles of the previous item's dV/dK store live in the dS^T buffer of this item's SECOND tile
@@ -539,17 +678,63 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mbar_wait(&sm.sdp_full[b], (gs >> 1) & 1);
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 1);
         tc_fence_after();
+        uint8_t* ds_atom = sm.ds[gi & 1] + (s & 1) * kTileBytes;
+#if LCBI_BWD_CHUNKED
+        // The 32 columns go through in four chunks of 8 inside a real (not unrolled) loop, so that the compiler cannot
+        // hoist all 32 MUFU.EX2 into one burst that blocks the warp for 256+ cycles: a chunk's packing / stores then
+        // issue while the sibling warp of the SM sub-partition owns the MUFU pipe. Chunks alternate between two
+        // register sets; the next chunk's TMEM load is in flight while the current one is processed.
+        {
+          const uint32_t t_s = tmem + lane_sel + kTmemS + b * kStep + hh * 32;
+          const uint32_t t_dp = tmem + lane_sel + kTmemDP + b * kStep + hh * 32;
+          auto chunk = [&](const uint32_t* sx, const uint32_t* dx, int col) {   // columns [col, col + 8) of this thread's 32
+            uint32_t pk4[4], ds4[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float p0 = fast_exp2(__uint_as_float(sx[e]) * c), p1 = fast_exp2(__uint_as_float(sx[e + 1]) * c);
+              pk4[e >> 1] = pack_bf16x2(p0, p1);
+              ds4[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dx[e]), p1 * __uint_as_float(dx[e + 1]));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + (col >> 3)))),
+                         "r"(ds4[0]), "r"(ds4[1]), "r"(ds4[2]), "r"(ds4[3]) : "memory");
+            // in place: 8 columns read -> 4 packed columns written at half the offset (always columns already consumed)
+            tmem_st_x4(t_s + (col >> 1), pk4);
+            tmem_st_x4(t_dp + (col >> 1), ds4);
+          };
+          uint32_t sa[8], da[8], sb[8], db[8];
+          tmem_ld_x8(t_s, sa);
+          tmem_ld_x8(t_dp, da);
+          tmem_ld_wait();
+#pragma unroll 1
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int c0 = k2 * 16;
+            tmem_ld_x8(t_s + c0 + 8, sb);
+            tmem_ld_x8(t_dp + c0 + 8, db);
+            chunk(sa, da, c0);
+            tmem_ld_wait();
+            if (k2 == 0) {
+              tmem_ld_x8(t_s + 16, sa);
+              tmem_ld_x8(t_dp + 16, da);
+            }
+            chunk(sb, db, c0 + 8);
+            tmem_ld_wait();
+          }
+        }
+#else
         uint32_t sv[32], dpv[32];
         tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + hh * 32, sv);
         tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
         tmem_ld_wait();
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 2);
         uint32_t pk[16], dsk[16];
-        uint8_t* ds_atom = sm.ds[gi & 1] + (s & 1) * kTileBytes;
         // the per-query terms were already added by the tensor core: sv = q.k - lse/scale, dpv = dO.v - D
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
+          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c);
+          // LCBI_BWD_POLY_EXP of every 32 exponentials run on the FMA pipe instead of the (16 / clk / SM) MUFU pipe
+          const bool poly = (LCBI_BWD_POLY_EXP == 16) || (LCBI_BWD_POLY_EXP == 8 && (e & 2)) ||
+                            (LCBI_BWD_POLY_EXP == 4 && (e & 6) == 6);
+          const float p1 = poly ? poly_exp2(__uint_as_float(sv[e + 1]) * c) : fast_exp2(__uint_as_float(sv[e + 1]) * c);
           pk[e >> 1] = pack_bf16x2(p0, p1);
           dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
         }
@@ -560,6 +745,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // in place: the packed results overwrite the first 16 of the 32 columns this thread just read
         tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + hh * 32, pk);
         tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dsk);
+#endif
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 3);
         tmem_st_wait();
         tc_fence_before();
@@ -569,6 +755,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 4);
       }
 
+#endif
       // The S^T / dP^T GEMMs of this item have all retired (this thread consumed the last of them), so K and V of the
       // next item can take their place in TMEM now: its first GEMMs then run while this item's epilogue drains dV / dK.
       LCBI_ITEM_T(3);
@@ -725,12 +912,14 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e);
   }
 
-  static bool attr_set = false;
+  static unsigned long long configured = 0;   // one bit per device ordinal
   const int smem_bytes = static_cast<int>(sizeof(BwdSmem)) + 1024;
-  if (!attr_set) {
+  if (first_launch_on_current_device(&configured)) {
     e = cudaFuncSetAttribute(dense_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(e);
-    attr_set = true;
+    if (e != cudaSuccess) {
+      configured = 0;
+      return set_cuda_error(e);
+    }
   }
   BwdParams p;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.Nq_pad = nq_pad;
@@ -740,13 +929,8 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   p.d_aug = reinterpret_cast<const __nv_bfloat16*>(d_aug);
   p.dq_acc = dq_acc;
   p.accumulate_dkv = a.accumulate_dkv;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return set_cuda_error(e);
-  }
+  const int num_sms = current_device_sm_count();
+  if (num_sms <= 0) return LCBI_ERR_CUDA;
   p.n_kv_tiles = (a.Nk + kTile - 1) / kTile;
   p.n_items = p.n_kv_tiles * a.H * a.B;
   const int slots = num_sms - reserved_sms() > 1 ? num_sms - reserved_sms() : 1;

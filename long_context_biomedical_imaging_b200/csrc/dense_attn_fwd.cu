@@ -400,20 +400,17 @@ int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream) {
       make_bhnd_map(&to, a.o, a.B, a.H, a.Nq, a.o_strides[0], a.o_strides[1], a.o_strides[2], kBlockM))
     return LCBI_ERR_TENSOR_MAP;
 
-  static bool attr_set = false;
+  static unsigned long long configured = 0;   // one bit per device ordinal
   const int smem_bytes = static_cast<int>(sizeof(FwdSmem)) + 1024;
-  if (!attr_set) {
+  if (first_launch_on_current_device(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(dense_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(e);
-    attr_set = true;
+    if (e != cudaSuccess) {
+      configured = 0;
+      return set_cuda_error(e);
+    }
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return set_cuda_error(e);
-  }
+  const int num_sms = current_device_sm_count();
+  if (num_sms <= 0) return LCBI_ERR_CUDA;
   FwdParams p;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
   p.n_q_tiles = (a.Nq + kBlockM - 1) / kBlockM;

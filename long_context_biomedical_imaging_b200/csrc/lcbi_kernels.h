@@ -40,6 +40,13 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream);
 // SMs the persistent dense kernels leave free (for communication kernels running beside them); capi.cu
 int reserved_sms();
 
+// Per-device launch state (capi.cu). cudaFuncSetAttribute applies to the CURRENT device only, so "already configured"
+// is remembered per device ordinal, not per process: one bit per device in a word owned by the kernel's launcher.
+// Returns true when the current device's bit was not set yet (and sets it).
+bool first_launch_on_current_device(unsigned long long* seen_mask);
+// SM count of the current device (cached per ordinal); <= 0 on error (text recorded for lcbi_last_error()).
+int current_device_sm_count();
+
 // patch embedding (patch_embed.cu). img_dims / patch / grid are (D, H, W)-ordered triples (D = 1 for 2-D).
 int patch_embed_fwd_launch(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
                            void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,

@@ -268,10 +268,32 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
         LCBI_R4(r, 20), LCBI_R4(r, 24), LCBI_R4(r, 28)
       : "r"(taddr));
 }
+// 16x256b.x8: the warp reads 16 TMEM lanes x 64 columns starting at the lane in taddr. Fragment layout (the mma.sync
+// accumulator layout, repeated per 8-column block j): thread t holds r[4j + 2v + e] = lane (t / 4 + 8v),
+// column 8j + 2 (t % 4) + e, so the four threads of a quad cover 32 contiguous bytes of one lane's fp32 row.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : LCBI_R4(r, 0), LCBI_R4(r, 4), LCBI_R4(r, 8), LCBI_R4(r, 12), LCBI_R4(r, 16),
+        LCBI_R4(r, 20), LCBI_R4(r, 24), LCBI_R4(r, 28)
+      : "r"(taddr));
+}
+// fire-and-forget fp32 pair add into global memory (one L2 atomic per 8 bytes; a quad's four pairs fill one sector)
+__device__ __forceinline__ void red_add_f32x2(float* gptr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gptr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_f32x4(float* gptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), LCBI_W4(r, 0) : "memory");
+}
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(
                    taddr),

@@ -258,11 +258,13 @@ win_attn_fwd_small_kernel(const WinParams p) {
 template <int D>
 int launch_small(const WinParams& p, cudaStream_t stream) {
   using L = SmallFwdSmem<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long configured = 0;   // one bit per device ordinal (one word per head_dim instantiation)
+  if (first_launch_on_current_device(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(win_attn_fwd_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return set_cuda_error(e);
-    attr_set = true;
+    if (e != cudaSuccess) {
+      configured = 0;
+      return set_cuda_error(e);
+    }
   }
   const int units = p.win_count;
   int grid_x = (2 * 148 * 4 + p.H - 1) / p.H;     // ~2 waves of persistent CTAs (4 per SM) per head slice

@@ -6,6 +6,9 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from long_context_biomedical_imaging_b200 import _lib  # noqa: E402
+if os.environ.get("LCBI_LIB_PATH"):          # an experimental build of the library (tools/ablate_dense.py build)
+    _lib.LIB_PATH = os.environ["LCBI_LIB_PATH"]
 from long_context_biomedical_imaging_b200 import ops  # noqa: E402
 
 
@@ -51,7 +54,7 @@ def run(B, H, N, do_bwd=True, time_it=False):
                 fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            iters = 10
+            iters = 30
             e0.record()
             for _ in range(iters):
                 fn()
