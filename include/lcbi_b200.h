@@ -145,6 +145,24 @@ int lcbi_win_attn_bwd_range(int ndim, const int* grid, const int* window, const 
 int lcbi_window_maps(int ndim, const int* grid, const int* window, const int* shift, int* gather, int* region,
                      int* relidx, int* n_out, int* nw_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the channel axis of token rows: the norm1 / norm2 that feed the qkv projection and the MLP in the
+ * encoder blocks (torch.nn.LayerNorm(hidden), model/models/backbone_vit.py:260-263 with the modules built at :249-258;
+ * backbone_swin.py:437,489-490). Statistics and arithmetic in fp32 (layer_norm is an autocast-to-fp32 op in the
+ * reference); the output is written directly in the dtype the following Linear consumes.
+ *   x  : (rows, C) contiguous fp32 or bf16, C % 4 == 0;  gamma, beta: (C) fp32 or NULL (no affine: the
+ *        F.layer_norm of backbone_swin.py:866-879);  y: (rows, C) fp32 or bf16;  mean, rstd: (rows) fp32 (saved
+ *        for the backward).
+ * Backward: dy like y, dx like x (NULL to skip), dgamma / dbeta (C) fp32 WRITTEN, not accumulated (NULL to skip
+ * both or either); the column reduction is deterministic (slab partials in `workspace`, summed in order).
+ * ---------------------------------------------------------------------------------------------- */
+int lcbi_layer_norm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int y_is_bf16,
+                        float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+size_t lcbi_layer_norm_bwd_workspace_bytes(int64_t rows, int C);
+int lcbi_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
+                        const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, void* workspace,
+                        size_t workspace_bytes, int64_t rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ from torch.nn import LayerNorm
 
 from . import ops
 from .blocks import MLPBlock as Mlp
-from .blocks import PatchEmbed
+from .blocks import PatchEmbed, apply_layer_norm
 
 _ALT_MIXER_MSG = ("use_hyena/use_mamba route to the reference's HyenaOperator / MambaVisionMixer "
                   "(model/models/hyena.py, mamba.py), which are outside the B200 attention hot path; build the "
@@ -225,10 +225,10 @@ class SwinTransformerBlock(nn.Module):
     def forward_part1(self, x, mask_matrix=None):
         """x: (B, [D,] H, W, C) channel-last. `mask_matrix` is accepted for signature parity and ignored: the
         kernel evaluates the shift-mask regions itself."""
-        return self.attn.forward_grid(self.norm1(x), self.shift_size)
+        return self.attn.forward_grid(apply_layer_norm(self.norm1, x), self.shift_size)
 
     def forward_part2(self, x):
-        return self.drop_path(self.mlp(self.norm2(x)))
+        return self.drop_path(self.mlp(apply_layer_norm(self.norm2, x)))
 
     def forward(self, x, mask_matrix=None):
         shortcut = x
@@ -266,7 +266,7 @@ class PatchMergingV2(nn.Module):
             if (h % 2) or (w % 2):
                 x = F.pad(x, (0, 0, 0, w % 2, 0, h % 2))
             x = torch.cat([x[:, j::2, i::2, :] for i, j in itertools.product(range(2), range(2))], -1)
-        return self.reduction(self.norm(x))
+        return self.reduction(apply_layer_norm(self.norm, x))
 
 
 MERGING_MODE = {"mergingv2": PatchMergingV2}
@@ -368,7 +368,11 @@ class SwinTransformer_with_alt_ops(nn.Module):
         return self._channel_first(F.layer_norm(x.permute(*perm_in), [x.shape[1]]))
 
     def _out(self, x_cl, normalize):
-        return self._channel_first(F.layer_norm(x_cl, [x_cl.shape[-1]]) if normalize else x_cl)
+        if not normalize:
+            return self._channel_first(x_cl)
+        if x_cl.is_cuda and x_cl.shape[-1] % 4 == 0:   # affine-free; fp32 out like the reference's autocast layer_norm
+            return self._channel_first(ops.layer_norm(x_cl, None, None, 1e-5, out_dtype=torch.float32))
+        return self._channel_first(F.layer_norm(x_cl, [x_cl.shape[-1]]))
 
     def forward(self, x, normalize=True):
         if self.spatial_dims == 2:

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .blocks import MLPBlock, PatchEmbeddingBlock
+from .blocks import MLPBlock, PatchEmbeddingBlock, apply_layer_norm
 
 _ALT_MIXER_MSG = ("use_hyena/use_mamba route to the reference's HyenaOperator / MambaVisionMixer "
                   "(model/models/hyena.py, mamba.py), which are outside the B200 attention hot path; build the "
@@ -120,8 +120,8 @@ class TransformerBlock(nn.Module):
         self.norm2 = nn.LayerNorm(hidden_size)
 
     def forward(self, x):
-        x = x + self.attn(self.norm1(x))
-        x = x + self.mlp(self.norm2(x))
+        x = x + self.attn(apply_layer_norm(self.norm1, x))
+        x = x + self.mlp(apply_layer_norm(self.norm2, x))
         return x
 
 
@@ -164,5 +164,5 @@ class ViT_with_alt_ops(nn.Module):
         for blk in self.blocks:
             x = blk(x)
             hidden_states_out.append(x)
-        hidden_states_out.append(self.norm(x))
+        hidden_states_out.append(apply_layer_norm(self.norm, x, out_dtype=x.dtype))   # a hidden state, not a Linear input
         return hidden_states_out

@@ -7,7 +7,8 @@ re-implemented with identical parameter names / shapes so state_dicts interchang
   MLPBlock             (backbone_vit.py:249, backbone_swin.py:433)         keys: linear1.*, linear2.*
 
 The two patch-embedding modules run the fused CUDA kernel (ops.patch_embed); MLPBlock is plain torch
-(adjacent component).
+(adjacent component). apply_layer_norm routes the blocks' nn.LayerNorm modules through the
+LayerNorm kernels (the normalisation in front of the qkv projection).
 """
 from __future__ import annotations
 
@@ -27,6 +28,18 @@ def ensure_tuple_rep(x, n):
             return tuple(int(x[0]) for _ in range(n))
         raise ValueError(f"sequence must have length {n}, got {len(x)}")
     return tuple(int(x) for _ in range(n))
+
+
+def apply_layer_norm(norm, x, out_dtype=None):
+    """`norm(x)` for the encoder blocks' nn.LayerNorm modules through the fused kernels (ops.layer_norm: fp32
+    statistics, output written in the dtype the next Linear consumes). The module keeps its parameters (state_dict
+    keys norm1 / norm2 / norm as in the reference: backbone_vit.py:249-258, backbone_swin.py:419-433); any other
+    norm_layer, or a channel count the kernel does not take, runs as the module itself."""
+    if (type(norm) is nn.LayerNorm and x.is_cuda and len(norm.normalized_shape) == 1 and
+            norm.normalized_shape[0] == x.shape[-1] and x.shape[-1] % 4 == 0):
+        return ops.layer_norm(x, norm.weight, norm.bias, norm.eps, out_dtype)
+    y = norm(x)
+    return y if out_dtype is None else y.to(out_dtype)
 
 
 class MLPBlock(nn.Module):

@@ -225,4 +225,33 @@ int lcbi_window_maps(int ndim, const int* grid, const int* window, const int* sh
                                        static_cast<cudaStream_t>(stream)), "lcbi_window_maps");
 }
 
+static int ln_status(int rc, const char* who) {
+  static thread_local char buf[256];
+  const char* why = nullptr;
+  if (rc == LCBI_ERR_UNSUPPORTED) why = "the channel count must be a multiple of 4";
+  if (rc == LCBI_ERR_BAD_ARG) why = "non-positive rows / channels, negative eps, or a pointer that is not 16-byte aligned";
+  if (rc == LCBI_ERR_WORKSPACE) why = "workspace missing, misaligned or smaller than lcbi_layer_norm_bwd_workspace_bytes";
+  if (!why) return rc;
+  std::snprintf(buf, sizeof(buf), "%s: %s", who, why);
+  return fail(rc, buf);
+}
+
+int lcbi_layer_norm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int y_is_bf16,
+                        float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+  if (!x || !y || !mean || !rstd) return fail(LCBI_ERR_BAD_ARG, "lcbi_layer_norm_fwd: null pointer argument");
+  return ln_status(layer_norm_fwd_launch(x, x_is_bf16, gamma, beta, y, y_is_bf16, mean, rstd, rows, C, eps,
+                                         static_cast<cudaStream_t>(stream)), "lcbi_layer_norm_fwd");
+}
+
+size_t lcbi_layer_norm_bwd_workspace_bytes(int64_t rows, int C) { return layer_norm_bwd_workspace_bytes(rows, C); }
+
+int lcbi_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
+                        const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, void* workspace,
+                        size_t workspace_bytes, int64_t rows, int C, void* stream) {
+  if (!dy || !x || !mean || !rstd) return fail(LCBI_ERR_BAD_ARG, "lcbi_layer_norm_bwd: null pointer argument");
+  return ln_status(layer_norm_bwd_launch(dy, dy_is_bf16, x, x_is_bf16, gamma, mean, rstd, dx, dgamma, dbeta,
+                                          static_cast<float*>(workspace), workspace_bytes, rows, C,
+                                          static_cast<cudaStream_t>(stream)), "lcbi_layer_norm_bwd");
+}
+
 }  // extern "C"

@@ -84,6 +84,10 @@ constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTme
 #ifndef LCBI_BWD_CHUNKED
 #define LCBI_BWD_CHUNKED 0
 #endif
+// > 0: exponentials and the products / packs that consume them are interleaved pair by pair, LAG pairs apart (see the loop)
+#ifndef LCBI_BWD_INTERLEAVE
+#define LCBI_BWD_INTERLEAVE 0
+#endif
 #ifndef LCBI_BWD_POLY_EXP
 #define LCBI_BWD_POLY_EXP 0
 #endif
@@ -149,6 +153,7 @@ struct BwdParams {
   const __nv_bfloat16* d_aug;     // likewise -D, D = rowsum(dO o O)
   float* dq_acc;       // fp32 (B,Nq,H,64) accumulator
   int accumulate_dkv;
+  uint32_t zero_bits;  // always 0; opaque to the compiler (LCBI_BWD_INTERLEAVE)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -728,6 +733,23 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 2);
         uint32_t pk[16], dsk[16];
         // the per-query terms were already added by the tensor core: sv = q.k - lse/scale, dpv = dO.v - D
+#if LCBI_BWD_INTERLEAVE
+        // Left alone, the compiler hoists all 32 MUFU.EX2 into one burst; the warp then sits on the 16 / clk / SM MUFU
+        // pipe for the whole burst and only afterwards multiplies, packs and stores, and its sibling warp on the SM
+        // sub-partition does the same in lockstep. A data dependency forces the interleave instead: the exponent of
+        // pair i gets (bits & 0) of the packed result of pair i - LAG added, with the 0 a kernel parameter the compiler
+        // cannot fold. The products / packs of one pair then issue under the MUFU time of the next ones.
+        uint32_t tok[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int i = e >> 1;
+          const float z = i >= LCBI_BWD_INTERLEAVE ? __uint_as_float(tok[i >= LCBI_BWD_INTERLEAVE ? i - LCBI_BWD_INTERLEAVE : 0]) : 0.0f;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c, z)), p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c, z));
+          pk[i] = pack_bf16x2(p0, p1);
+          dsk[i] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
+          tok[i] = (pk[i] | dsk[i]) & p.zero_bits;
+        }
+#else
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float p0 = fast_exp2(__uint_as_float(sv[e]) * c);
@@ -738,6 +760,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           pk[e >> 1] = pack_bf16x2(p0, p1);
           dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
         }
+#endif
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
@@ -929,6 +952,7 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   p.d_aug = reinterpret_cast<const __nv_bfloat16*>(d_aug);
   p.dq_acc = dq_acc;
   p.accumulate_dkv = a.accumulate_dkv;
+  p.zero_bits = 0u;
   const int num_sms = current_device_sm_count();
   if (num_sms <= 0) return LCBI_ERR_CUDA;
   p.n_kv_tiles = (a.Nk + kTile - 1) / kTile;

@@ -1,0 +1,292 @@
+// LayerNorm over the channel axis of token rows, forward and backward, for sm_100a.
+//
+// The normalisations that bracket the attention kernels in the reference's encoder blocks: `self.norm1(x)` in front
+// of the qkv projection and `self.norm2(x)` in front of the MLP (/root/reference/model/models/backbone_vit.py:260-263,
+// backbone_swin.py:437,489-490), torch.nn.LayerNorm(hidden) with eps 1e-5 evaluated in fp32 (layer_norm is an
+// autocast-to-fp32 op). Here the forward writes the normalised rows directly in the dtype the following Linear
+// consumes (bf16 under bf16 autocast: the same round-to-nearest the autocast cast applies to the fp32 result, minus
+// one full-tensor cast kernel), and the backward is two HBM-bound kernels: dx row by row, and d(gamma) / d(beta) as
+// a column reduction over row slabs followed by a small deterministic sum of the slab partials (no atomics).
+//   fwd       : y = (x - mean) * rstd * gamma + beta                       warp = row
+//   bwd (dx)  : dx = rstd * (g dy - mean_c(g dy) - xhat mean_c(g dy xhat))  warp = row
+//   bwd (g,b) : dgamma_c = sum_r dy xhat, dbeta_c = sum_r dy               CTA = 128 columns x one slab of rows
+// Rows are C contiguous elements (C % 4 == 0), fp32 or bf16 in, fp32 or bf16 out; statistics in fp32, two-pass
+// variance (mean first, then centred squares) like the reference's kernel.
+#include <cuda_bf16.h>
+
+#include "lcbi_kernels.h"
+
+namespace lcbi {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kCache = 8;   // float4 per lane kept in registers: rows up to 1024 channels are read from memory once
+constexpr int kCacheDx = 6; // the dx kernel keeps two values per element: 768 channels in registers, 3 CTAs per SM
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a);
+  o.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C,
+              float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const TX* xr = x + r * C;
+  const int nvec = C >> 2;
+  float4 cache[kCache];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCache; ++i) {
+    const int v = lane + 32 * i;
+    cache[i] = v < nvec ? load4(xr + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (cache[i].x + cache[i].y) + (cache[i].z + cache[i].w);
+  }
+  for (int v = lane + 32 * kCache; v < nvec; v += 32) {
+    const float4 t = load4(xr + 4 * v);
+    s += (t.x + t.y) + (t.z + t.w);
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCache; ++i) {
+    if (lane + 32 * i < nvec) {
+      const float a = cache[i].x - mean, b = cache[i].y - mean, c = cache[i].z - mean, d = cache[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  for (int v = lane + 32 * kCache; v < nvec; v += 32) {
+    const float4 t = load4(xr + 4 * v);
+    const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+  if (lane == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+  }
+  TY* yr = y + r * C;
+  auto emit = [&](int v, float4 t) {
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gamma != nullptr) g = load4(gamma + 4 * v);
+    if (beta != nullptr) b = load4(beta + 4 * v);
+    store4(yr + 4 * v, make_float4((t.x - mean) * rstd * g.x + b.x, (t.y - mean) * rstd * g.y + b.y,
+                                   (t.z - mean) * rstd * g.z + b.z, (t.w - mean) * rstd * g.w + b.w));
+  };
+#pragma unroll
+  for (int i = 0; i < kCache; ++i)
+    if (lane + 32 * i < nvec) emit(lane + 32 * i, cache[i]);
+  for (int v = lane + 32 * kCache; v < nvec; v += 32) emit(v, load4(xr + 4 * v));
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+ln_bwd_dx_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TX* __restrict__ dx,
+                 int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const TX* xr = x + r * C;
+  const TY* dyr = dy + r * C;
+  const int nvec = C >> 2;
+  const float mean = mean_in[r], rstd = rstd_in[r];
+  // per element: w = gamma * dy, h = xhat
+  auto wh = [&](int v, float4& w, float4& h) {
+    const float4 t = load4(xr + 4 * v), d = load4(dyr + 4 * v);
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gamma != nullptr) g = load4(gamma + 4 * v);
+    w = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+    h = make_float4((t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd);
+  };
+  float4 cw[kCacheDx], ch[kCacheDx];
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCacheDx; ++i) {
+    if (lane + 32 * i < nvec) {
+      wh(lane + 32 * i, cw[i], ch[i]);
+      a += (cw[i].x + cw[i].y) + (cw[i].z + cw[i].w);
+      b += (cw[i].x * ch[i].x + cw[i].y * ch[i].y) + (cw[i].z * ch[i].z + cw[i].w * ch[i].w);
+    }
+  }
+  for (int v = lane + 32 * kCacheDx; v < nvec; v += 32) {
+    float4 w, h;
+    wh(v, w, h);
+    a += (w.x + w.y) + (w.z + w.w);
+    b += (w.x * h.x + w.y * h.y) + (w.z * h.z + w.w * h.w);
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  a = warp_sum(a) * inv_c;
+  b = warp_sum(b) * inv_c;
+  TX* dxr = dx + r * C;
+  auto emit = [&](int v, const float4& w, const float4& h) {
+    store4(dxr + 4 * v, make_float4(rstd * (w.x - a - h.x * b), rstd * (w.y - a - h.y * b), rstd * (w.z - a - h.z * b),
+                                    rstd * (w.w - a - h.w * b)));
+  };
+#pragma unroll
+  for (int i = 0; i < kCacheDx; ++i)
+    if (lane + 32 * i < nvec) emit(lane + 32 * i, cw[i], ch[i]);
+  for (int v = lane + 32 * kCacheDx; v < nvec; v += 32) {
+    float4 w, h;
+    wh(v, w, h);
+    emit(v, w, h);
+  }
+}
+
+// d(gamma), d(beta) partials: CTA (32 x 8 threads) = 128 columns x the rows of slab blockIdx.y; thread (tx, ty) walks
+// rows ty, ty + 8, ... of the slab with four columns in registers, then the 8 row lanes are summed through shared
+// memory and written to partial[slab][2][C].
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+ln_bwd_params_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, float* __restrict__ partial, int64_t rows, int C,
+                     int64_t rows_per_slab) {
+  __shared__ float4 sg[8][32], sb[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 4;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_slab;
+  const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < C) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float mean = mean_in[r], rstd = rstd_in[r];
+      const float4 t = load4(x + r * C + col), d = load4(dy + r * C + col);
+      g.x += d.x * (t.x - mean) * rstd; g.y += d.y * (t.y - mean) * rstd;
+      g.z += d.z * (t.z - mean) * rstd; g.w += d.w * (t.w - mean) * rstd;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+  }
+  sg[ty][tx] = g;
+  sb[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && col < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 g2 = sg[k][tx], b2 = sb[k][tx];
+      g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+      b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+    }
+    float* out = partial + static_cast<int64_t>(blockIdx.y) * 2 * C;
+    store4(out + col, g);
+    store4(out + C + col, b);
+  }
+}
+
+__global__ void ln_bwd_params_finish_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int C, int slabs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * C) return;
+  float s = 0.f;
+  for (int k = 0; k < slabs; ++k) s += partial[static_cast<int64_t>(k) * 2 * C + c];
+  if (c < C) {
+    if (dgamma != nullptr) dgamma[c] = s;
+  } else if (dbeta != nullptr) {
+    dbeta[c - C] = s;
+  }
+}
+
+int param_slabs(int64_t rows, int C) {
+  const int col_blocks = (C + 127) / 128;
+  int64_t slabs = (4 * 148 + col_blocks - 1) / col_blocks;   // ~4 CTAs per SM in total
+  const int64_t max_slabs = (rows + 63) / 64;                // at least 64 rows per slab
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  return static_cast<int>(slabs);
+}
+
+template <typename TX, typename TY>
+int fwd_typed(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows,
+              int C, float eps, cudaStream_t stream) {
+  const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
+  ln_fwd_kernel<TX, TY><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+      static_cast<const TX*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps);
+  return set_cuda_error(cudaGetLastError());
+}
+
+template <typename TX, typename TY>
+int bwd_typed(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+              float* dgamma, float* dbeta, float* workspace, int64_t rows, int C, cudaStream_t stream) {
+  if (dx != nullptr) {
+    const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    ln_bwd_dx_kernel<TX, TY><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+        static_cast<const TY*>(dy), static_cast<const TX*>(x), gamma, mean, rstd, static_cast<TX*>(dx), rows, C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  if (dgamma != nullptr || dbeta != nullptr) {
+    const int slabs = param_slabs(rows, C);
+    const int64_t rows_per_slab = (rows + slabs - 1) / slabs;
+    dim3 grid((C + 127) / 128, slabs);
+    ln_bwd_params_kernel<TX, TY><<<grid, 256, 0, stream>>>(static_cast<const TY*>(dy), static_cast<const TX*>(x), mean,
+                                                           rstd, workspace, rows, C, rows_per_slab);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+    ln_bwd_params_finish_kernel<<<(2 * C + 255) / 256, 256, 0, stream>>>(workspace, dgamma, dbeta, C, slabs);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  return LCBI_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+size_t layer_norm_bwd_workspace_bytes(int64_t rows, int C) {
+  if (rows <= 0 || C <= 0) return 0;
+  return static_cast<size_t>(param_slabs(rows, C)) * 2 * C * sizeof(float);
+}
+
+int layer_norm_fwd_launch(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int y_is_bf16,
+                          float* mean, float* rstd, int64_t rows, int C, float eps, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0 || !(eps >= 0.f)) return LCBI_ERR_BAD_ARG;
+  if (C % 4 != 0 || rows > (int64_t(1) << 31) * kWarpsPerCta) return LCBI_ERR_UNSUPPORTED;
+  // rows of bf16 start on 8-byte boundaries when C % 4 == 0; the base pointers must be 16-byte aligned
+  if (!aligned16(x) || !aligned16(y) || (gamma && !aligned16(gamma)) || (beta && !aligned16(beta))) return LCBI_ERR_BAD_ARG;
+  if (x_is_bf16) {
+    return y_is_bf16 ? fwd_typed<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, y, mean, rstd, rows, C, eps, stream)
+                     : fwd_typed<__nv_bfloat16, float>(x, gamma, beta, y, mean, rstd, rows, C, eps, stream);
+  }
+  return y_is_bf16 ? fwd_typed<float, __nv_bfloat16>(x, gamma, beta, y, mean, rstd, rows, C, eps, stream)
+                   : fwd_typed<float, float>(x, gamma, beta, y, mean, rstd, rows, C, eps, stream);
+}
+
+int layer_norm_bwd_launch(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                          float* workspace, size_t workspace_bytes, int64_t rows, int C, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0) return LCBI_ERR_BAD_ARG;
+  if (C % 4 != 0 || rows > (int64_t(1) << 31) * kWarpsPerCta) return LCBI_ERR_UNSUPPORTED;
+  if (!aligned16(dy) || !aligned16(x) || (dx && !aligned16(dx)) || (gamma && !aligned16(gamma))) return LCBI_ERR_BAD_ARG;
+  if ((dgamma != nullptr || dbeta != nullptr) &&
+      (workspace == nullptr || !aligned16(workspace) || workspace_bytes < layer_norm_bwd_workspace_bytes(rows, C)))
+    return LCBI_ERR_WORKSPACE;
+  if (x_is_bf16) {
+    return dy_is_bf16 ? bwd_typed<__nv_bfloat16, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, C, stream)
+                      : bwd_typed<__nv_bfloat16, float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, C, stream);
+  }
+  return dy_is_bf16 ? bwd_typed<float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, C, stream)
+                    : bwd_typed<float, float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, C, stream);
+}
+
+}  // namespace lcbi

@@ -94,4 +94,12 @@ int window_maps_launch(int ndim, const int* grid, const int* window, const int* 
 int attn_merge_launch(float* acc, float* lse_acc, const void* o_s, const float* lse_s, void* out_bf16, int B, int N,
                       int H, int head_dim, int first, cudaStream_t stream);
 
+// LayerNorm over the channel axis (layer_norm.cu)
+int layer_norm_fwd_launch(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int y_is_bf16,
+                          float* mean, float* rstd, int64_t rows, int C, float eps, cudaStream_t stream);
+size_t layer_norm_bwd_workspace_bytes(int64_t rows, int C);
+int layer_norm_bwd_launch(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                          float* workspace, size_t workspace_bytes, int64_t rows, int C, cudaStream_t stream);
+
 }  // namespace lcbi

@@ -136,6 +136,82 @@ def dense_attention_qkv(qkv, num_heads, scale=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# LayerNorm in front of the qkv projection / the MLP
+# --------------------------------------------------------------------------------------------------
+def _is_bf16(t):
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise ValueError(f"layer_norm handles fp32 and bf16 tensors, got {t.dtype}")
+
+
+class _LayerNorm(torch.autograd.Function):
+    """x: (..., C) fp32 / bf16 -> y in `out_dtype`; statistics in fp32 (lcbi_layer_norm_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rc = _lib.load().lcbi_layer_norm_fwd(_p(x), _is_bf16(x), _p(weight) if weight is not None else None,
+                                             _p(bias) if bias is not None else None, _p(y), _is_bf16(y), _p(mean),
+                                             _p(rstd), rows, C, float(eps), _stream())
+        _lib.check(rc, "lcbi_layer_norm_fwd")
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dy = dy.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        need_w = weight is not None and ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty((C,), dtype=torch.float32, device=x.device) if need_w else None
+        db = torch.empty((C,), dtype=torch.float32, device=x.device) if need_b else None
+        lib = _lib.load()
+        ws, ws_bytes = None, 0
+        if need_w or need_b:
+            ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+        if need_dx or need_w or need_b:
+            rc = lib.lcbi_layer_norm_bwd(_p(dy), _is_bf16(dy), _p(x), _is_bf16(x),
+                                         _p(weight) if weight is not None else None, _p(mean), _p(rstd),
+                                         _p(dx) if need_dx else None, _p(dw) if need_w else None,
+                                         _p(db) if need_b else None, _p(ws) if ws is not None else None, ws_bytes,
+                                         rows, C, _stream())
+            _lib.check(rc, "lcbi_layer_norm_bwd")
+        return dx, dw, db, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
+    """Drop-in for `nn.LayerNorm(C)(x)` as the encoder blocks call it (reference backbone_vit.py:260-263,
+    backbone_swin.py:437,489). `out_dtype` defaults to bf16 under bf16 autocast (what the following Linear would cast
+    the fp32 result to anyway) and to x.dtype otherwise."""
+    _require_cuda(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if out_dtype is None:
+        amp_bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        out_dtype = torch.bfloat16 if amp_bf16 else x.dtype
+    if x.shape[-1] % 4 != 0:
+        raise ValueError("layer_norm needs a channel count that is a multiple of 4")
+    if weight is not None and (weight.dtype != torch.float32 or not weight.is_contiguous()):
+        weight = weight.float().contiguous()
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        bias = bias.float().contiguous()
+    return _LayerNorm.apply(x, weight, bias, float(eps), out_dtype)
+
+
+# --------------------------------------------------------------------------------------------------
 # patch embedding
 # --------------------------------------------------------------------------------------------------
 def _triple(vals):

@@ -9,6 +9,7 @@ Restates, from the reference's algorithm (citations into /root/reference/model/m
   * SwinTransformerBlock.forward_part1     backbone_swin.py:435-487  -> swin_part1 (gather/scatter form)
   * MONAI 1.3.0 PatchEmbeddingBlock / PatchEmbed (absent third-party dependency, requirements.txt:5;
     call sites backbone_vit.py:351-361,383 and backbone_swin.py:800-806,885) -> patch_embed_vit / _swin
+  * torch.nn.LayerNorm as applied by the blocks   backbone_vit.py:260-263, backbone_swin.py:437,489 -> layer_norm_rows
 
 Pinned against outputs of the unmodified reference run in the build container
 (oracle/make_golden.py -> tests/golden/*.npz; checked in tests/test_oracle_golden.py).
@@ -183,6 +184,24 @@ def patch_embed_swin(img, weight, bias):
 # ------------------------------------------------------------------------------------------------
 # deterministic parameter fill shared by the golden generator and the tests
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# LayerNorm in front of the qkv projection / the MLP
+# ------------------------------------------------------------------------------------------------
+def layer_norm_rows(x, weight=None, bias=None, eps=1e-5):
+    """torch.nn.LayerNorm(C) as the encoder blocks apply it to token rows (norm1 / norm2 at backbone_vit.py:260-263,
+    backbone_swin.py:437,489; modules built at backbone_vit.py:249-258): per row, mean and BIASED variance over the
+    channel axis, (x - mean) / sqrt(var + eps), then the affine. Written out (not F.layer_norm) so that the test
+    that pins it against torch.nn.LayerNorm means something."""
+    mean = x.mean(dim=-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(dim=-1, keepdim=True)
+    y = (x - mean) / torch.sqrt(var + eps)
+    if weight is not None:
+        y = y * weight
+    if bias is not None:
+        y = y + bias
+    return y
+
+
 def fill_parameters_(module, seed, std=0.05):
     """Overwrites every floating-point parameter with seeded N(0, std) values (LayerNorm weights get
     1 + N(0, std)), in state_dict order. Integer buffers are left alone. Makes golden fixtures

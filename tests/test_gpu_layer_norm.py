@@ -1,0 +1,111 @@
+"""GPU parity of the LayerNorm kernels (lcbi_layer_norm_fwd / _bwd through ops.layer_norm) against the CPU oracle's
+written-out LayerNorm (oracle.attention_oracle.layer_norm_rows, pinned against torch.nn.LayerNorm in
+tests/test_oracle_golden.py): the norm1 / norm2 of the encoder blocks (reference backbone_vit.py:260-263,
+backbone_swin.py:437,489).
+
+Tolerances (max-rel = max|a-b| / max|b|): fp32 in / fp32 out 1e-5 (budget of the fp32-accumulate path: 1e-4);
+bf16 output or bf16 input 1e-2 (budget of the bf16 path: 2e-2; one bf16 rounding is 3.9e-3)."""
+import pytest
+import torch
+
+from conftest import max_rel
+from oracle import attention_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(rows_shape, C, x_dtype, out_dtype, affine, seed=0):
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(seed)
+    x = (torch.randn(*rows_shape, C) * 1.7 + 0.3).to(x_dtype)
+    w = (1 + 0.3 * torch.randn(C)) if affine else None
+    b = (0.3 * torch.randn(C)) if affine else None
+    g = torch.randn(*rows_shape, C).to(out_dtype)
+
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True) if affine else None
+    br = b.double().requires_grad_(True) if affine else None
+    yr = ao.layer_norm_rows(xr, wr, br, 1e-5)
+    ref_grads = torch.autograd.grad(yr, (xr, wr, br) if affine else (xr,), g.double())
+
+    xd = x.cuda().requires_grad_(True)
+    wd = w.cuda().requires_grad_(True) if affine else None
+    bd = b.cuda().requires_grad_(True) if affine else None
+    y = ops.layer_norm(xd, wd, bd, 1e-5, out_dtype=out_dtype)
+    assert y.dtype == out_dtype and y.shape == x.shape
+    grads = torch.autograd.grad(y, (xd, wd, bd) if affine else (xd,), g.cuda())
+    tol = 1e-5 if (x_dtype == torch.float32 and out_dtype == torch.float32) else 1e-2
+    assert max_rel(y.detach().float().cpu(), yr.detach()) < tol
+    assert grads[0].dtype == x_dtype
+    for got, ref, name in zip(grads, ref_grads, ("dx", "dgamma", "dbeta")):
+        assert max_rel(got.float().cpu(), ref) < tol, (name, max_rel(got.float().cpu(), ref))
+
+
+@pytest.mark.parametrize("rows_shape,C", [((1,), 4), ((77,), 48), ((2, 197), 192), ((3, 5, 7), 96), ((1, 1728), 768),
+                                          ((300,), 1536), ((9,), 3072)])
+@pytest.mark.parametrize("affine", [True, False])
+def test_layer_norm_fp32_vs_oracle(rows_shape, C, affine):
+    _case(rows_shape, C, torch.float32, torch.float32, affine)
+
+
+@pytest.mark.parametrize("x_dtype,out_dtype", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                               (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("rows_shape,C", [((2, 197), 192), ((1, 1728), 768), ((64,), 1536)])
+def test_layer_norm_mixed_dtypes_vs_oracle(rows_shape, C, x_dtype, out_dtype):
+    _case(rows_shape, C, x_dtype, out_dtype, True, seed=1)
+
+
+def test_layer_norm_rejects_what_the_kernel_does_not_take():
+    from long_context_biomedical_imaging_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.layer_norm(torch.randn(4, 8), None, None)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        ops.layer_norm(torch.randn(4, 6, device="cuda"), None, None)
+
+
+def test_layer_norm_under_autocast_feeds_the_linear_in_bf16_and_matches_torch():
+    """Inside bf16 autocast the op emits bf16 — the rounding torch's autocast applies to its fp32 LayerNorm output in
+    front of a Linear — so block-level results agree with nn.LayerNorm -> nn.Linear to bf16 rounding."""
+    from long_context_biomedical_imaging_b200.blocks import apply_layer_norm
+
+    torch.manual_seed(2)
+    ln = torch.nn.LayerNorm(192).cuda()
+    lin = torch.nn.Linear(192, 64).cuda()
+    x = torch.randn(2, 50, 192, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = apply_layer_norm(ln, x)
+        assert y.dtype == torch.bfloat16
+        ours = lin(y)
+        theirs = lin(ln(x))
+        hidden = apply_layer_norm(ln, x, out_dtype=x.dtype)
+    assert hidden.dtype == torch.float32
+    assert max_rel(ours.detach().float().cpu(), theirs.detach().float().cpu()) < 1e-2
+    assert max_rel(hidden.detach().cpu(), ln(x).detach().cpu()) < 1e-5
+
+
+def test_layer_norm_full_size_properties():
+    """cfg3 encoder size (16 volumes x 1728 tokens x 768 channels): rows come out with zero mean / unit variance
+    (no affine), the backward is linear in dy, d(beta) is the column sum of dy, and dx is orthogonal to the
+    constant vector and to xhat row by row."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(4)
+    rows, C = 16 * 1728, 768
+    x = (torch.randn(rows, C, device="cuda") * 3 + 1).requires_grad_(True)
+    y = ops.layer_norm(x, None, None, 1e-5, out_dtype=torch.float32)
+    assert float(y.mean(-1).abs().max()) < 1e-5
+    assert float((y.var(-1, unbiased=False) - 1).abs().max()) < 1e-4
+    w = (1 + 0.2 * torch.randn(C, device="cuda")).requires_grad_(True)
+    b = torch.zeros(C, device="cuda", requires_grad=True)
+    g1, g2 = torch.randn(rows, C, device="cuda"), torch.randn(rows, C, device="cuda")
+    out = ops.layer_norm(x, w, b, 1e-5, out_dtype=torch.float32)
+    d1 = torch.autograd.grad(out, (x, w, b), g1, retain_graph=True)
+    d2 = torch.autograd.grad(out, (x, w, b), g2, retain_graph=True)
+    d12 = torch.autograd.grad(out, (x, w, b), 2 * g1 - 3 * g2)
+    for a, c, both in zip(d1, d2, d12):
+        assert max_rel((2 * a - 3 * c).cpu(), both.cpu()) < 1e-5
+    assert max_rel(d1[2].cpu(), g1.sum(0).cpu()) < 1e-5
+    assert float(d1[0].sum(-1).abs().max()) < 1e-3 * float(d1[0].abs().max()) * C ** 0.5
+    assert float((d1[0] * y.detach()).sum(-1).abs().max()) < 1e-3 * float(d1[0].abs().max()) * C ** 0.5

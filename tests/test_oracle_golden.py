@@ -103,3 +103,29 @@ def test_dense_attention_rows_matches_full():
     assert max_rel(rows.float(), full[[0, 17, 299]]) < 1e-5
     ref_lse = torch.logsumexp((q[[0, 17, 299]] @ k.T) * 0.125, -1)
     assert max_rel(lse.float(), ref_lse) < 1e-5
+
+
+def test_layer_norm_restatement_matches_the_reference_module_class():
+    """The blocks' norm1 / norm2 are torch.nn.LayerNorm (reference backbone_vit.py:249-258): the oracle's written-out
+    LayerNorm must agree with that class, outputs and all three gradients, in fp64."""
+    import torch
+
+    from oracle import attention_oracle as ao
+
+    torch.manual_seed(3)
+    for rows, C in [(5, 48), (7, 192), (3, 768), (2, 1536)]:
+        ln = torch.nn.LayerNorm(C).double()
+        with torch.no_grad():
+            ln.weight.normal_(1.0, 0.3)
+            ln.bias.normal_(0.0, 0.3)
+        x = (torch.randn(rows, C, dtype=torch.float64) * 2 + 0.5).requires_grad_(True)
+        g = torch.randn(rows, C, dtype=torch.float64)
+        ref = ln(x)
+        ref_grads = torch.autograd.grad(ref, (x, ln.weight, ln.bias), g)
+        w, b = ln.weight.detach().clone().requires_grad_(True), ln.bias.detach().clone().requires_grad_(True)
+        x2 = x.detach().clone().requires_grad_(True)
+        out = ao.layer_norm_rows(x2, w, b, ln.eps)
+        grads = torch.autograd.grad(out, (x2, w, b), g)
+        assert max_rel(out.detach().numpy(), ref.detach().numpy()) < 1e-12
+        for a, r in zip(grads, ref_grads):
+            assert max_rel(a.numpy(), r.numpy()) < 1e-11

@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, "long_context_biomedical_imaging_b200", "csrc")
 BWD_MASKS = [int(x) for x in os.environ.get("ABL_BWD", "").split(",") if x != ""]   # backward switches existed up to commit a07535e
 FWD_MASKS = [int(x) for x in os.environ.get("ABL_FWD", "0,1,2,3,4").split(",") if x != ""]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-lineinfo", "-Xcompiler", "-fPIC"]
-OTHERS = ["capi", "dense_attn_fwd", "dense_attn_bwd", "window_attn", "window_attn_small", "patch_embed", "patch_embed_mma", "attn_merge"]
+OTHERS = ["capi", "dense_attn_fwd", "dense_attn_bwd", "window_attn", "window_attn_small", "patch_embed", "patch_embed_mma", "attn_merge", "layer_norm"]
 
 
 def lib_path(kind, mask):

@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "long_context_biomedical_imaging_b200", "csrc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-lineinfo",
          "-Xcompiler", "-fPIC"]
 OBJS = ["capi", "dense_attn_fwd", "dense_attn_bwd", "window_attn", "window_attn_small", "patch_embed",
-        "patch_embed_mma", "attn_merge"]
+        "patch_embed_mma", "attn_merge", "layer_norm"]
 # name -> (source file, extra defines)
 VARIANTS = {
     "base": ("dense_attn_bwd", []),
@@ -31,6 +31,9 @@ VARIANTS = {
     "red2s6poly8": ("dense_attn_bwd", ["-DLCBI_BWD_DQ_RED=2", "-DLCBI_BWD_QSTAGES=6", "-DLCBI_BWD_POLY_EXP=8"]),
     "split": ("dense_attn_bwd", ["-DLCBI_BWD_SPLIT_STEPS=1"]),
     "chunked": ("dense_attn_bwd", ["-DLCBI_BWD_CHUNKED=1"]),
+    "il2": ("dense_attn_bwd", ["-DLCBI_BWD_INTERLEAVE=2"]),
+    "il3": ("dense_attn_bwd", ["-DLCBI_BWD_INTERLEAVE=3"]),
+    "il4": ("dense_attn_bwd", ["-DLCBI_BWD_INTERLEAVE=4"]),
 }
 
 
