@@ -163,6 +163,14 @@ int lcbi_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_
                         const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, void* workspace,
                         size_t workspace_bytes, int64_t rows, int C, void* stream);
 
+/* Bias gradient of the token-wise Linear layers that bracket the attention kernels (qkv with bias at
+ * backbone_swin.py:309, out_proj / proj at backbone_vit.py:167,202 and backbone_swin.py:311,358, the MLP's
+ * linear1 / linear2): dbias (C) fp32 = column sums of dy (rows, C) fp32 or bf16, C % 4 == 0, WRITTEN not accumulated.
+ * Deterministic (slab partials summed in order); `workspace` as for lcbi_layer_norm_bwd
+ * (lcbi_layer_norm_bwd_workspace_bytes(rows, C)). The GEMMs of those layers stay cuBLAS. */
+int lcbi_bias_grad(const void* dy, int dy_is_bf16, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows,
+                   int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,10 +176,10 @@ class WindowAttention(nn.Module):
     def forward_grid(self, x, shift_size):
         """x: (B, *grid, C) normed tokens on the un-padded grid -> (B, *grid, C). The whole of the reference's
         pad/roll/partition -> attention -> reverse/roll/crop chain."""
-        qkv = self.qkv(x)
+        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
         o = ops.window_attention(qkv, self.qkv.bias, self.relative_position_bias_table, x.shape[1:-1],
                                  self.window_size, shift_size, self.num_heads, self.scale)
-        return self.proj(o)
+        return ops.linear(o, self.proj.weight, self.proj.bias)
 
     def forward(self, x, mask):
         """Reference seam on pre-partitioned windows (B*nW, n, C). Only mask=None is expressible without the token

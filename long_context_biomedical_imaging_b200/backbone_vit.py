@@ -99,7 +99,7 @@ class SABlock(nn.Module):
     def forward(self, x):
         qkv = self.qkv(x)                                        # (B, N, 3C), feature = s*C + h*d + j
         o = ops.dense_attention_qkv(qkv, self.num_heads, self.scale)   # (B, N, C), feature = h*d + j
-        return self.out_proj(o)
+        return ops.linear(o, self.out_proj.weight, self.out_proj.bias)   # cuBLAS GEMMs, fused-kernel bias gradient
 
 
 class TransformerBlock(nn.Module):

@@ -59,7 +59,8 @@ class MLPBlock(nn.Module):
         self.drop2 = nn.Dropout(dropout_rate)
 
     def forward(self, x):
-        return self.drop2(self.linear2(self.drop1(self.fn(self.linear1(x)))))
+        h = self.fn(ops.linear(x, self.linear1.weight, self.linear1.bias))
+        return self.drop2(ops.linear(self.drop1(h), self.linear2.weight, self.linear2.bias))
 
 
 def _conv_like_init_(weight, bias):

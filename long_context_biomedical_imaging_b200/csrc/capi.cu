@@ -254,4 +254,11 @@ int lcbi_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_
                                           static_cast<cudaStream_t>(stream)), "lcbi_layer_norm_bwd");
 }
 
+int lcbi_bias_grad(const void* dy, int dy_is_bf16, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows,
+                   int C, void* stream) {
+  if (!dy || !dbias) return fail(LCBI_ERR_BAD_ARG, "lcbi_bias_grad: null pointer argument");
+  return ln_status(bias_grad_launch(dy, dy_is_bf16, dbias, static_cast<float*>(workspace), workspace_bytes, rows, C,
+                                    static_cast<cudaStream_t>(stream)), "lcbi_bias_grad");
+}
+
 }  // extern "C"

@@ -14,6 +14,8 @@
 // variance (mean first, then centred squares) like the reference's kernel.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "lcbi_kernels.h"
 
 namespace lcbi {
@@ -193,16 +195,190 @@ ln_bwd_params_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const 
   }
 }
 
+// sum of the slab partials, one warp per output column (dgamma columns first, then dbeta): lanes take slabs
+// lane, lane + 32, ... and are combined by a fixed shuffle tree, so the result does not depend on timing
 __global__ void ln_bwd_params_finish_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta, int C, int slabs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= 2 * C) return;
   float s = 0.f;
-  for (int k = 0; k < slabs; ++k) s += partial[static_cast<int64_t>(k) * 2 * C + c];
-  if (c < C) {
-    if (dgamma != nullptr) dgamma[c] = s;
-  } else if (dbeta != nullptr) {
-    dbeta[c - C] = s;
+  for (int k = threadIdx.x & 31; k < slabs; k += 32) s += partial[static_cast<int64_t>(k) * 2 * C + c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) {
+    if (c < C) {
+      if (dgamma != nullptr) dgamma[c] = s;
+    } else if (dbeta != nullptr) {
+      dbeta[c - C] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Narrow rows (C <= 128: Swin stage-1 tokens, 48 / 96 / 128 channels). One warp per row would leave most lanes idle
+// and give every warp a few hundred bytes of work, so LPR lanes (a power of two >= C / 4) share a row, a warp holds
+// 32 / LPR rows side by side, and every warp walks kNarrowIter such row groups with all their loads issued up front.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNarrowIter = 4;
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TX, typename TY, int LPR>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ln_fwd_narrow_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows,
+                     int C, float eps) {
+  constexpr int kRpw = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const bool active = sub < (C >> 2);
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t row0 = warp * (kRpw * kNarrowIter) + lane / LPR;
+  float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active && gamma != nullptr) g = load4(gamma + 4 * sub);
+  if (active && beta != nullptr) b = load4(beta + 4 * sub);
+  float4 v[kNarrowIter];
+#pragma unroll
+  for (int it = 0; it < kNarrowIter; ++it) {
+    const int64_t r = row0 + it * kRpw;
+    v[it] = (active && r < rows) ? load4(x + r * C + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+#pragma unroll
+  for (int it = 0; it < kNarrowIter; ++it) {
+    const int64_t r = row0 + it * kRpw;
+    const float mean = group_sum<LPR>((v[it].x + v[it].y) + (v[it].z + v[it].w)) * inv_c;
+    const float dx0 = v[it].x - mean, dx1 = v[it].y - mean, dx2 = v[it].z - mean, dx3 = v[it].w - mean;
+    const float q = active ? (dx0 * dx0 + dx1 * dx1) + (dx2 * dx2 + dx3 * dx3) : 0.f;
+    const float rstd = rsqrtf(group_sum<LPR>(q) * inv_c + eps);
+    if (r < rows) {
+      if (sub == 0) {
+        mean_out[r] = mean;
+        rstd_out[r] = rstd;
+      }
+      if (active)
+        store4(y + r * C + 4 * sub, make_float4(dx0 * rstd * g.x + b.x, dx1 * rstd * g.y + b.y, dx2 * rstd * g.z + b.z,
+                                               dx3 * rstd * g.w + b.w));
+    }
+  }
+}
+
+template <typename TX, typename TY, int LPR>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ln_bwd_dx_narrow_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TX* __restrict__ dx,
+                        int64_t rows, int C) {
+  constexpr int kRpw = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const bool active = sub < (C >> 2);
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t row0 = warp * (kRpw * kNarrowIter) + lane / LPR;
+  float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (active && gamma != nullptr) g = load4(gamma + 4 * sub);
+  float4 xv[kNarrowIter], dv[kNarrowIter];
+  float mean[kNarrowIter], rstd[kNarrowIter];
+#pragma unroll
+  for (int it = 0; it < kNarrowIter; ++it) {
+    const int64_t r = row0 + it * kRpw;
+    const bool ok = active && r < rows;
+    xv[it] = ok ? load4(x + r * C + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dv[it] = ok ? load4(dy + r * C + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    mean[it] = r < rows ? mean_in[r] : 0.f;
+    rstd[it] = r < rows ? rstd_in[r] : 0.f;
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+#pragma unroll
+  for (int it = 0; it < kNarrowIter; ++it) {
+    const int64_t r = row0 + it * kRpw;
+    const float4 w = make_float4(dv[it].x * g.x, dv[it].y * g.y, dv[it].z * g.z, dv[it].w * g.w);
+    float4 h = make_float4((xv[it].x - mean[it]) * rstd[it], (xv[it].y - mean[it]) * rstd[it],
+                           (xv[it].z - mean[it]) * rstd[it], (xv[it].w - mean[it]) * rstd[it]);
+    if (!active) h = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float a = group_sum<LPR>((w.x + w.y) + (w.z + w.w)) * inv_c;
+    const float b = group_sum<LPR>((w.x * h.x + w.y * h.y) + (w.z * h.z + w.w * h.w)) * inv_c;
+    if (active && r < rows)
+      store4(dx + r * C + 4 * sub, make_float4(rstd[it] * (w.x - a - h.x * b), rstd[it] * (w.y - a - h.y * b),
+                                              rstd[it] * (w.z - a - h.z * b), rstd[it] * (w.w - a - h.w * b)));
+  }
+}
+
+// d(gamma), d(beta) partials for narrow rows: the CTA's 256 threads tile (rows x C/4 column vectors) densely — thread t
+// owns column vector t % nvec of rows t / nvec, t / nvec + 256 / nvec, ... of its slab — so consecutive threads read
+// consecutive addresses whatever C is; the row lanes are then summed through shared memory in a fixed order.
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+ln_bwd_params_narrow_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
+                            const float* __restrict__ rstd_in, float* __restrict__ partial, int64_t rows, int C,
+                            int64_t rows_per_slab) {
+  __shared__ float4 sg[256], sb[256];
+  const int nvec = C >> 2;
+  const int rows_per_iter = 256 / nvec;
+  const int t = threadIdx.x, cv = t % nvec, rl = t / nvec;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_slab;
+  const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < rows_per_iter) {
+    for (int64_t r = r0 + rl; r < r1; r += rows_per_iter) {
+      const float mean = mean_in[r], rstd = rstd_in[r];
+      const float4 xt = load4(x + r * C + 4 * cv), d = load4(dy + r * C + 4 * cv);
+      g.x += d.x * (xt.x - mean) * rstd; g.y += d.y * (xt.y - mean) * rstd;
+      g.z += d.z * (xt.z - mean) * rstd; g.w += d.w * (xt.w - mean) * rstd;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+  }
+  sg[t] = g;
+  sb[t] = b;
+  __syncthreads();
+  if (t < nvec) {
+    for (int k = 1; k < rows_per_iter; ++k) {
+      const float4 g2 = sg[t + k * nvec], b2 = sb[t + k * nvec];
+      g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+      b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+    }
+    float* out = partial + static_cast<int64_t>(blockIdx.x) * 2 * C;
+    store4(out + 4 * t, g);
+    store4(out + C + 4 * t, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums of a (rows, C) matrix: the bias gradient of a token-wise Linear (db = sum over tokens of dY), which
+// autograd otherwise computes with a generic reduction that costs as much as the LayerNorm kernels above. Same slab
+// scheme and the same deterministic finish as d(gamma) / d(beta); the partial buffer's second half stays unused.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ a, float* __restrict__ partial, int64_t rows, int C, int64_t rows_per_slab) {
+  __shared__ float4 ss[256];
+  const int nvec = C >> 2;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_slab;
+  const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // wide rows: thread (tx, ty) = column vector blockIdx.x * 32 + tx, rows ty, ty + 8, ...; narrow rows (C <= 128, one
+  // column block): the 256 threads tile (rows x column vectors) densely
+  const bool narrow = nvec <= 32;
+  const int lanes_per_row = narrow ? nvec : 32;
+  const int rows_per_iter = narrow ? 256 / nvec : 8;
+  const int t = threadIdx.x;
+  const int cv = narrow ? t % nvec : blockIdx.x * 32 + (t & 31);
+  const int rl = narrow ? t / nvec : t >> 5;
+  if (cv < nvec && rl < rows_per_iter) {
+    for (int64_t r = r0 + rl; r < r1; r += rows_per_iter) {
+      const float4 v = load4(a + r * C + 4 * cv);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  ss[t] = acc;
+  __syncthreads();
+  if (rl == 0 && cv < nvec) {
+    for (int k = 1; k < rows_per_iter; ++k) {
+      const float4 v = ss[t + k * lanes_per_row];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    store4(partial + static_cast<int64_t>(blockIdx.y) * 2 * C + 4 * cv, acc);
   }
 }
 
@@ -218,6 +394,19 @@ int param_slabs(int64_t rows, int C) {
 template <typename TX, typename TY>
 int fwd_typed(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows,
               int C, float eps, cudaStream_t stream) {
+  if (C <= 128) {
+    auto launch = [&](auto lpr) {
+      constexpr int LPR = decltype(lpr)::value;
+      const int64_t rows_per_cta = static_cast<int64_t>(kWarpsPerCta) * (32 / LPR) * kNarrowIter;
+      const int64_t blocks = (rows + rows_per_cta - 1) / rows_per_cta;
+      ln_fwd_narrow_kernel<TX, TY, LPR><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+          static_cast<const TX*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps);
+    };
+    if (C <= 32) launch(std::integral_constant<int, 8>{});
+    else if (C <= 64) launch(std::integral_constant<int, 16>{});
+    else launch(std::integral_constant<int, 32>{});
+    return set_cuda_error(cudaGetLastError());
+  }
   const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
   ln_fwd_kernel<TX, TY><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
       static_cast<const TX*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps);
@@ -227,7 +416,20 @@ int fwd_typed(const void* x, const float* gamma, const float* beta, void* y, flo
 template <typename TX, typename TY>
 int bwd_typed(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
               float* dgamma, float* dbeta, float* workspace, int64_t rows, int C, cudaStream_t stream) {
-  if (dx != nullptr) {
+  if (dx != nullptr && C <= 128) {
+    auto launch = [&](auto lpr) {
+      constexpr int LPR = decltype(lpr)::value;
+      const int64_t rows_per_cta = static_cast<int64_t>(kWarpsPerCta) * (32 / LPR) * kNarrowIter;
+      const int64_t blocks = (rows + rows_per_cta - 1) / rows_per_cta;
+      ln_bwd_dx_narrow_kernel<TX, TY, LPR><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+          static_cast<const TY*>(dy), static_cast<const TX*>(x), gamma, mean, rstd, static_cast<TX*>(dx), rows, C);
+    };
+    if (C <= 32) launch(std::integral_constant<int, 8>{});
+    else if (C <= 64) launch(std::integral_constant<int, 16>{});
+    else launch(std::integral_constant<int, 32>{});
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  } else if (dx != nullptr) {
     const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
     ln_bwd_dx_kernel<TX, TY><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
         static_cast<const TY*>(dy), static_cast<const TX*>(x), gamma, mean, rstd, static_cast<TX*>(dx), rows, C);
@@ -237,12 +439,17 @@ int bwd_typed(const void* dy, const void* x, const float* gamma, const float* me
   if (dgamma != nullptr || dbeta != nullptr) {
     const int slabs = param_slabs(rows, C);
     const int64_t rows_per_slab = (rows + slabs - 1) / slabs;
-    dim3 grid((C + 127) / 128, slabs);
-    ln_bwd_params_kernel<TX, TY><<<grid, 256, 0, stream>>>(static_cast<const TY*>(dy), static_cast<const TX*>(x), mean,
-                                                           rstd, workspace, rows, C, rows_per_slab);
+    if (C <= 128) {
+      ln_bwd_params_narrow_kernel<TX, TY><<<slabs, 256, 0, stream>>>(static_cast<const TY*>(dy), static_cast<const TX*>(x),
+                                                                     mean, rstd, workspace, rows, C, rows_per_slab);
+    } else {
+      dim3 grid((C + 127) / 128, slabs);
+      ln_bwd_params_kernel<TX, TY><<<grid, 256, 0, stream>>>(static_cast<const TY*>(dy), static_cast<const TX*>(x), mean,
+                                                             rstd, workspace, rows, C, rows_per_slab);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
-    ln_bwd_params_finish_kernel<<<(2 * C + 255) / 256, 256, 0, stream>>>(workspace, dgamma, dbeta, C, slabs);
+    ln_bwd_params_finish_kernel<<<(2 * C + 7) / 8, 256, 0, stream>>>(workspace, dgamma, dbeta, C, slabs);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
   }
@@ -256,6 +463,27 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 size_t layer_norm_bwd_workspace_bytes(int64_t rows, int C) {
   if (rows <= 0 || C <= 0) return 0;
   return static_cast<size_t>(param_slabs(rows, C)) * 2 * C * sizeof(float);
+}
+
+int bias_grad_launch(const void* dy, int dy_is_bf16, float* dbias, float* workspace, size_t workspace_bytes,
+                     int64_t rows, int C, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0) return LCBI_ERR_BAD_ARG;
+  if (C % 4 != 0) return LCBI_ERR_UNSUPPORTED;
+  if (!aligned16(dy) || !aligned16(dbias)) return LCBI_ERR_BAD_ARG;
+  if (workspace == nullptr || !aligned16(workspace) || workspace_bytes < layer_norm_bwd_workspace_bytes(rows, C))
+    return LCBI_ERR_WORKSPACE;
+  const int slabs = param_slabs(rows, C);
+  const int64_t rows_per_slab = (rows + slabs - 1) / slabs;
+  dim3 grid((C + 127) / 128, slabs);
+  if (dy_is_bf16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), workspace, rows, C, rows_per_slab);
+  else
+    colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), workspace, rows, C, rows_per_slab);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
+  // only the first C columns of each slab's partial row carry data: sum those into dbias
+  ln_bwd_params_finish_kernel<<<(C + 7) / 8, 256, 0, stream>>>(workspace, dbias, nullptr, C, slabs);
+  return set_cuda_error(cudaGetLastError());
 }
 
 int layer_norm_fwd_launch(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int y_is_bf16,

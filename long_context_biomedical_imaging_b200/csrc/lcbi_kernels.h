@@ -102,4 +102,7 @@ int layer_norm_bwd_launch(const void* dy, int dy_is_bf16, const void* x, int x_i
                           const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                           float* workspace, size_t workspace_bytes, int64_t rows, int C, cudaStream_t stream);
 
+int bias_grad_launch(const void* dy, int dy_is_bf16, float* dbias, float* workspace, size_t workspace_bytes,
+                     int64_t rows, int C, cudaStream_t stream);
+
 }  // namespace lcbi

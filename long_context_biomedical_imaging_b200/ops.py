@@ -212,6 +212,70 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# token-wise Linear with a bias: cuBLAS GEMMs, bias gradient through lcbi_bias_grad
+# --------------------------------------------------------------------------------------------------
+def bias_grad(dy):
+    """Column sums of dy viewed as (rows, C): the bias gradient of a token-wise Linear. Returns fp32 (C)."""
+    _require_cuda(dy)
+    dy = dy.contiguous()
+    C = dy.shape[-1]
+    rows = dy.numel() // C
+    lib = _lib.load()
+    out = torch.empty((C,), dtype=torch.float32, device=dy.device)
+    ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dy.device)
+    rc = lib.lcbi_bias_grad(_p(dy), _is_bf16(dy), _p(out), _p(ws), ws_bytes, rows, C, _stream())
+    _lib.check(rc, "lcbi_bias_grad")
+    return out
+
+
+class _LinearBias(torch.autograd.Function):
+    """y = x W^T + b with the dtype flow of nn.Linear under autocast (operands in the compute dtype, fp32 accumulate in
+    cuBLAS, output in the compute dtype). The backward runs the two GEMMs in the same dtype as autograd would and the
+    bias gradient through lcbi_bias_grad instead of a generic reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, compute_dtype):
+        xc = x if x.dtype == compute_dtype else x.to(compute_dtype)
+        wc = weight if weight.dtype == compute_dtype else weight.to(compute_dtype)
+        bc = bias if bias.dtype == compute_dtype else bias.to(compute_dtype)
+        ctx.save_for_backward(xc, wc)
+        ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype)
+        return torch.nn.functional.linear(xc, wc, bc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc = ctx.saved_tensors
+        x_dtype, w_dtype, b_dtype = ctx.in_dtypes
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ wc).view(xc.shape).to(x_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = (dy2.t() @ xc.reshape(-1, xc.shape[-1])).to(w_dtype)
+        if ctx.needs_input_grad[2]:
+            db = bias_grad(dy2).to(b_dtype)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias):
+    """Drop-in for `nn.Linear(...)(x)` with a bias on CUDA tensors (the projections around the attention kernels and
+    the MLP: reference backbone_vit.py:167,202,249; backbone_swin.py:309-311,433)."""
+    if bias is None or not x.is_cuda or bias.shape[0] % 4 != 0 or x.dtype not in (torch.float32, torch.bfloat16):
+        return torch.nn.functional.linear(x, weight, bias)
+    if torch.is_autocast_enabled():
+        compute_dtype = torch.get_autocast_gpu_dtype()
+        if compute_dtype != torch.bfloat16:
+            return torch.nn.functional.linear(x, weight, bias)
+    else:
+        compute_dtype = torch.promote_types(x.dtype, weight.dtype)
+        if compute_dtype not in (torch.float32, torch.bfloat16):
+            return torch.nn.functional.linear(x, weight, bias)
+    with torch.autocast("cuda", enabled=False):
+        return _LinearBias.apply(x, weight, bias, compute_dtype)
+
+
+# --------------------------------------------------------------------------------------------------
 # patch embedding
 # --------------------------------------------------------------------------------------------------
 def _triple(vals):

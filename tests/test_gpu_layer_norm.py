@@ -43,7 +43,7 @@ def _case(rows_shape, C, x_dtype, out_dtype, affine, seed=0):
 
 
 @pytest.mark.parametrize("rows_shape,C", [((1,), 4), ((77,), 48), ((2, 197), 192), ((3, 5, 7), 96), ((1, 1728), 768),
-                                          ((300,), 1536), ((9,), 3072)])
+                                          ((300,), 1536), ((9,), 3072), ((33,), 32), ((130,), 64), ((1000,), 128), ((5000,), 132)])
 @pytest.mark.parametrize("affine", [True, False])
 def test_layer_norm_fp32_vs_oracle(rows_shape, C, affine):
     _case(rows_shape, C, torch.float32, torch.float32, affine)
@@ -109,3 +109,46 @@ def test_layer_norm_full_size_properties():
     assert max_rel(d1[2].cpu(), g1.sum(0).cpu()) < 1e-5
     assert float(d1[0].sum(-1).abs().max()) < 1e-3 * float(d1[0].abs().max()) * C ** 0.5
     assert float((d1[0] * y.detach()).sum(-1).abs().max()) < 1e-3 * float(d1[0].abs().max()) * C ** 0.5
+
+
+@pytest.mark.parametrize("rows_shape,cin,cout", [((3, 50), 96, 288), ((1, 1728), 768, 768), ((700,), 48, 144),
+                                                 ((5, 7, 9), 64, 4), ((2049,), 32, 520)])
+@pytest.mark.parametrize("autocast", [True, False])
+def test_linear_with_bias_matches_nn_linear(rows_shape, cin, cout, autocast):
+    """ops.linear = nn.Linear's GEMMs (same dtype flow) + lcbi_bias_grad for db: outputs and the three gradients
+    against torch.nn.functional.linear on the same tensors, same autocast state. bf16: 1e-2 max-rel (the bias
+    gradient is summed in fp32 here, in bf16-rounded form by autograd); fp32: 1e-5."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(5)
+    x = torch.randn(*rows_shape, cin, device="cuda", requires_grad=True)
+    w = (torch.randn(cout, cin, device="cuda") * cin ** -0.5).requires_grad_(True)
+    b = torch.randn(cout, device="cuda", requires_grad=True)
+    g = torch.randn(*rows_shape, cout, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        y = ops.linear(x, w, b)
+        yr = torch.nn.functional.linear(x, w, b)
+    assert y.dtype == yr.dtype
+    grads = torch.autograd.grad(y, (x, w, b), g.to(y.dtype))
+    ref = torch.autograd.grad(yr, (x, w, b), g.to(yr.dtype))
+    tol = 1e-2 if autocast else 1e-5
+    assert max_rel(y.detach().float().cpu(), yr.detach().float().cpu()) < tol
+    for got, want, name in zip(grads, ref, ("dx", "dw", "db")):
+        assert got.dtype == want.dtype, name
+        assert max_rel(got.float().cpu(), want.float().cpu()) < tol, (name, max_rel(got.float().cpu(), want.float().cpu()))
+    # the bias gradient against an fp64 column sum of exactly the dy the kernel saw
+    exact = g.to(y.dtype).double().reshape(-1, cout).sum(0)
+    assert max_rel(grads[2].double().cpu(), exact.cpu()) < 1e-5
+
+
+def test_bias_grad_full_size():
+    """Swin cfg2 stage-1 qkv gradient size (16 x 128 x 128 tokens x 288) in bf16, and a ViT cfg3 MLP size."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(6)
+    for rows, C in [(16 * 128 * 128, 288), (16 * 1728, 3072)]:
+        dy = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+        got = ops.bias_grad(dy)
+        want = dy.double().sum(0)
+        assert max_rel(got.double().cpu(), want.cpu()) < 1e-5
+        assert torch.equal(got, ops.bias_grad(dy))   # deterministic
