@@ -163,6 +163,20 @@ int lcbi_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_
                         const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, void* workspace,
                         size_t workspace_bytes, int64_t rows, int C, void* stream);
 
+/* The same LayerNorm fused with the residual add in front of it: the blocks compute `x = x + branch(...)` and then
+ * normalise the sum (backbone_vit.py:261-262 `x = x + self.attn(self.norm1(x)); x = x + self.mlp(self.norm2(x))`, the
+ * next block's norm1 or the encoder's final norm :395 following). Forward: xsum = x + delta (written, in x's dtype: the
+ * new residual stream and hidden state), y = LayerNorm(xsum). Backward: dx = dxsum + dLayerNorm(dy) where dxsum (may be
+ * NULL) is the gradient arriving at xsum from everything else that reads it; the same total is written as ddelta in
+ * delta's dtype (NULL to skip). Rows of at least 128 channels (C % 4 == 0); other arguments as above. */
+int lcbi_add_layer_norm_fwd(const void* x, int x_is_bf16, const void* delta, int delta_is_bf16, void* xsum,
+                            const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean, float* rstd,
+                            int64_t rows, int C, float eps, void* stream);
+int lcbi_add_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* dxsum, const void* xsum, int x_is_bf16,
+                            const float* gamma, const float* mean, const float* rstd, void* dx, void* ddelta,
+                            int delta_is_bf16, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                            int64_t rows, int C, void* stream);
+
 /* Bias gradient of the token-wise Linear layers that bracket the attention kernels (qkv with bias at
  * backbone_swin.py:309, out_proj / proj at backbone_vit.py:167,202 and backbone_swin.py:311,358, the MLP's
  * linear1 / linear2): dbias (C) fp32 = column sums of dy (rows, C) fp32 or bf16, C % 4 == 0, WRITTEN not accumulated.

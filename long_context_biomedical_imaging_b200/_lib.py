@@ -49,6 +49,11 @@ SIGNATURES = {
     "lcbi_layer_norm_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
     "lcbi_layer_norm_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                            c_vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int, c_vp]),
+    "lcbi_add_layer_norm_fwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
+                                               c_vp, c_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_float, c_vp]),
+    "lcbi_add_layer_norm_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                               ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64,
+                                               ctypes.c_int, c_vp]),
     "lcbi_bias_grad": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int, c_vp]),
     "lcbi_set_reserved_sms": (ctypes.c_int, [ctypes.c_int]),
     "lcbi_window_maps": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_i32p, c_i32p, c_vp]),

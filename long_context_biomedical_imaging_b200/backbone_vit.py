@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .blocks import MLPBlock, PatchEmbeddingBlock, apply_layer_norm
+from .blocks import MLPBlock, PatchEmbeddingBlock, apply_add_layer_norm, apply_layer_norm
 
 _ALT_MIXER_MSG = ("use_hyena/use_mamba route to the reference's HyenaOperator / MambaVisionMixer "
                   "(model/models/hyena.py, mamba.py), which are outside the B200 attention hot path; build the "
@@ -120,9 +120,8 @@ class TransformerBlock(nn.Module):
         self.norm2 = nn.LayerNorm(hidden_size)
 
     def forward(self, x):
-        x = x + self.attn(apply_layer_norm(self.norm1, x))
-        x = x + self.mlp(apply_layer_norm(self.norm2, x))
-        return x
+        x, y = apply_add_layer_norm(self.norm2, x, self.attn(apply_layer_norm(self.norm1, x)))   # x + attn, norm2 of it
+        return x + self.mlp(y)
 
 
 class ViT_with_alt_ops(nn.Module):
@@ -161,8 +160,18 @@ class ViT_with_alt_ops(nn.Module):
         x = self.patch_embedding(x)
         if hasattr(self, "cls_token"):
             x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype), x), dim=1)
+        # The blocks' arithmetic (reference :260-263) with every residual add folded into the LayerNorm that reads the
+        # sum: a block's MLP output stays pending until the next block's norm1 (or the final norm) adds it, and that
+        # fused pass also produces the block's hidden state. blk(x) itself remains the per-block seam.
+        pending = None
         for blk in self.blocks:
-            x = blk(x)
+            x, y = apply_add_layer_norm(blk.norm1, x, pending)
+            if pending is not None:
+                hidden_states_out.append(x)
+            x, y = apply_add_layer_norm(blk.norm2, x, blk.attn(y))
+            pending = blk.mlp(y)
+        x, y = apply_add_layer_norm(self.norm, x, pending, out_dtype=x.dtype)   # final norm: a hidden state, keeps x's dtype
+        if pending is not None:
             hidden_states_out.append(x)
-        hidden_states_out.append(apply_layer_norm(self.norm, x, out_dtype=x.dtype))   # a hidden state, not a Linear input
+        hidden_states_out.append(y)
         return hidden_states_out

@@ -42,6 +42,18 @@ def apply_layer_norm(norm, x, out_dtype=None):
     return y if out_dtype is None else y.to(out_dtype)
 
 
+def apply_add_layer_norm(norm, x, delta, out_dtype=None):
+    """(x + delta, norm(x + delta)): the residual add of a pre-norm block together with the LayerNorm that consumes the
+    sum (reference backbone_vit.py:261-262). `delta=None` means there is nothing to add yet (first block)."""
+    if delta is None:
+        return x, apply_layer_norm(norm, x, out_dtype)
+    if (type(norm) is nn.LayerNorm and x.is_cuda and len(norm.normalized_shape) == 1 and
+            norm.normalized_shape[0] == x.shape[-1]):
+        return ops.add_layer_norm(x, delta, norm.weight, norm.bias, norm.eps, out_dtype)
+    x = x + delta
+    return x, apply_layer_norm(norm, x, out_dtype)
+
+
 class MLPBlock(nn.Module):
     """linear1 -> GELU -> linear2 (all dropouts are 0 on the reference's reachable paths)."""
 

@@ -254,6 +254,32 @@ int lcbi_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_
                                           static_cast<cudaStream_t>(stream)), "lcbi_layer_norm_bwd");
 }
 
+int lcbi_add_layer_norm_fwd(const void* x, int x_is_bf16, const void* delta, int delta_is_bf16, void* xsum,
+                            const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean, float* rstd,
+                            int64_t rows, int C, float eps, void* stream) {
+  if (!x || !delta || !xsum || !y || !mean || !rstd)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_add_layer_norm_fwd: null pointer argument");
+  const int rc = add_layer_norm_fwd_launch(x, x_is_bf16, delta, delta_is_bf16, xsum, gamma, beta, y, y_is_bf16, mean,
+                                           rstd, rows, C, eps, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_UNSUPPORTED)
+    return fail(rc, "lcbi_add_layer_norm_fwd: the channel count must be a multiple of 4 and at least 128");
+  return ln_status(rc, "lcbi_add_layer_norm_fwd");
+}
+
+int lcbi_add_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* dxsum, const void* xsum, int x_is_bf16,
+                            const float* gamma, const float* mean, const float* rstd, void* dx, void* ddelta,
+                            int delta_is_bf16, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                            int64_t rows, int C, void* stream) {
+  if (!dy || !xsum || !mean || !rstd || !dx)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_add_layer_norm_bwd: null pointer argument");
+  const int rc = add_layer_norm_bwd_launch(dy, dy_is_bf16, dxsum, xsum, x_is_bf16, gamma, mean, rstd, dx, ddelta,
+                                           delta_is_bf16, dgamma, dbeta, static_cast<float*>(workspace),
+                                           workspace_bytes, rows, C, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_UNSUPPORTED)
+    return fail(rc, "lcbi_add_layer_norm_bwd: the channel count must be a multiple of 4 and at least 128");
+  return ln_status(rc, "lcbi_add_layer_norm_bwd");
+}
+
 int lcbi_bias_grad(const void* dy, int dy_is_bf16, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows,
                    int C, void* stream) {
   if (!dy || !dbias) return fail(LCBI_ERR_BAD_ARG, "lcbi_bias_grad: null pointer argument");

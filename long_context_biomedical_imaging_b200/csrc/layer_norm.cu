@@ -41,32 +41,59 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   o.y = *reinterpret_cast<const uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = o;
 }
+// the value a float4 has after a round trip through storage type T (identity for fp32)
+template <typename T>
+__device__ __forceinline__ float4 load4_rounded(float4 v) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  } else {
+    return v;
+  }
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-template <typename TX, typename TY>
+// With `delta` (the residual-branch output: attention or MLP result) the kernel first forms the new residual stream
+// xsum = x + delta, rounded to x's dtype exactly like the reference's `x = x + self.attn(...)` (backbone_vit.py:261-262),
+// writes it out, and normalises THAT: the block's residual add costs no pass of its own. The later passes re-read xsum.
+template <typename TX, typename TY, typename TD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+ln_fwd_kernel(const TX* __restrict__ x, const TD* __restrict__ delta, TX* __restrict__ xsum,
+              const float* __restrict__ gamma, const float* __restrict__ beta,
               TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C,
               float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (r >= rows) return;
-  const TX* xr = x + r * C;
+  const TX* xin = x + r * C;
+  // what the later passes read for rows longer than the register cache: the sum this thread wrote, if there is one
+  const TX* xr = delta != nullptr ? xsum + r * C : xin;
   const int nvec = C >> 2;
+  auto fetch = [&](int v) {
+    float4 t = load4(xin + 4 * v);
+    if (delta != nullptr) {
+      const float4 d = load4(delta + r * C + 4 * v);
+      t = make_float4(t.x + d.x, t.y + d.y, t.z + d.z, t.w + d.w);
+      store4(xsum + r * C + 4 * v, t);
+      t = load4_rounded<TX>(t);
+    }
+    return t;
+  };
   float4 cache[kCache];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kCache; ++i) {
     const int v = lane + 32 * i;
-    cache[i] = v < nvec ? load4(xr + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cache[i] = v < nvec ? fetch(v) : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (cache[i].x + cache[i].y) + (cache[i].z + cache[i].w);
   }
   for (int v = lane + 32 * kCache; v < nvec; v += 32) {
-    const float4 t = load4(xr + 4 * v);
+    const float4 t = fetch(v);
     s += (t.x + t.y) + (t.z + t.w);
   }
   const float mean = warp_sum(s) / static_cast<float>(C);
@@ -102,11 +129,14 @@ ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const f
   for (int v = lane + 32 * kCache; v < nvec; v += 32) emit(v, load4(xr + 4 * v));
 }
 
-template <typename TX, typename TY>
+// Backward of the fused form: `dres` (gradient arriving at xsum from everything downstream of the residual stream,
+// may be null) is added to the LayerNorm's dx, and the total is written twice, as the gradient of x (TX) and as the
+// gradient of delta (TD, may be null) — the add's backward and the dtype cast cost no passes of their own either.
+template <typename TX, typename TY, typename TD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 ln_bwd_dx_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TX* __restrict__ dx,
-                 int64_t rows, int C) {
+                 const TX* __restrict__ dres, TD* __restrict__ ddelta, int64_t rows, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -143,8 +173,14 @@ ln_bwd_dx_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const floa
   b = warp_sum(b) * inv_c;
   TX* dxr = dx + r * C;
   auto emit = [&](int v, const float4& w, const float4& h) {
-    store4(dxr + 4 * v, make_float4(rstd * (w.x - a - h.x * b), rstd * (w.y - a - h.y * b), rstd * (w.z - a - h.z * b),
-                                    rstd * (w.w - a - h.w * b)));
+    float4 o = make_float4(rstd * (w.x - a - h.x * b), rstd * (w.y - a - h.y * b), rstd * (w.z - a - h.z * b),
+                           rstd * (w.w - a - h.w * b));
+    if (dres != nullptr) {
+      const float4 e = load4(dres + r * C + 4 * v);
+      o = make_float4(o.x + e.x, o.y + e.y, o.z + e.z, o.w + e.w);
+    }
+    store4(dxr + 4 * v, o);
+    if (ddelta != nullptr) store4(ddelta + r * C + 4 * v, o);
   };
 #pragma unroll
   for (int i = 0; i < kCacheDx; ++i)
@@ -408,8 +444,28 @@ int fwd_typed(const void* x, const float* gamma, const float* beta, void* y, flo
     return set_cuda_error(cudaGetLastError());
   }
   const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-  ln_fwd_kernel<TX, TY><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
-      static_cast<const TX*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps);
+  ln_fwd_kernel<TX, TY, TX><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+      static_cast<const TX*>(x), nullptr, nullptr, gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps);
+  return set_cuda_error(cudaGetLastError());
+}
+
+template <typename TX, typename TY, typename TD>
+int add_fwd_typed(const void* x, const void* delta, void* xsum, const float* gamma, const float* beta, void* y,
+                  float* mean, float* rstd, int64_t rows, int C, float eps, cudaStream_t stream) {
+  const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
+  ln_fwd_kernel<TX, TY, TD><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+      static_cast<const TX*>(x), static_cast<const TD*>(delta), static_cast<TX*>(xsum), gamma, beta,
+      static_cast<TY*>(y), mean, rstd, rows, C, eps);
+  return set_cuda_error(cudaGetLastError());
+}
+
+template <typename TX, typename TY, typename TD>
+int add_bwd_dx_typed(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
+                     void* dx, const void* dres, void* ddelta, int64_t rows, int C, cudaStream_t stream) {
+  const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
+  ln_bwd_dx_kernel<TX, TY, TD><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+      static_cast<const TY*>(dy), static_cast<const TX*>(xsum), gamma, mean, rstd, static_cast<TX*>(dx),
+      static_cast<const TX*>(dres), static_cast<TD*>(ddelta), rows, C);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -431,8 +487,9 @@ int bwd_typed(const void* dy, const void* x, const float* gamma, const float* me
     if (e != cudaSuccess) return set_cuda_error(e);
   } else if (dx != nullptr) {
     const int64_t blocks = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-    ln_bwd_dx_kernel<TX, TY><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
-        static_cast<const TY*>(dy), static_cast<const TX*>(x), gamma, mean, rstd, static_cast<TX*>(dx), rows, C);
+    ln_bwd_dx_kernel<TX, TY, TX><<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, 0, stream>>>(
+        static_cast<const TY*>(dy), static_cast<const TX*>(x), gamma, mean, rstd, static_cast<TX*>(dx), nullptr, nullptr,
+        rows, C);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e);
   }
@@ -463,6 +520,45 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 size_t layer_norm_bwd_workspace_bytes(int64_t rows, int C) {
   if (rows <= 0 || C <= 0) return 0;
   return static_cast<size_t>(param_slabs(rows, C)) * 2 * C * sizeof(float);
+}
+
+// fused residual add + LayerNorm (rows of at least 128 channels; the narrow-row kernels have no fused form)
+int add_layer_norm_fwd_launch(const void* x, int x_is_bf16, const void* delta, int delta_is_bf16, void* xsum,
+                              const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean, float* rstd,
+                              int64_t rows, int C, float eps, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0 || !(eps >= 0.f)) return LCBI_ERR_BAD_ARG;
+  if (C % 4 != 0 || C < 128) return LCBI_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(delta) || !aligned16(xsum) || !aligned16(y) || (gamma && !aligned16(gamma)) ||
+      (beta && !aligned16(beta)))
+    return LCBI_ERR_BAD_ARG;
+#define LCBI_LN_DISPATCH3(FN, ...)                                                                            \
+  (x_is_bf16 ? (y_is_bf16 ? (delta_is_bf16 ? FN<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(__VA_ARGS__)     \
+                                           : FN<__nv_bfloat16, __nv_bfloat16, float>(__VA_ARGS__))            \
+                          : (delta_is_bf16 ? FN<__nv_bfloat16, float, __nv_bfloat16>(__VA_ARGS__)             \
+                                           : FN<__nv_bfloat16, float, float>(__VA_ARGS__)))                   \
+             : (y_is_bf16 ? (delta_is_bf16 ? FN<float, __nv_bfloat16, __nv_bfloat16>(__VA_ARGS__)             \
+                                           : FN<float, __nv_bfloat16, float>(__VA_ARGS__))                    \
+                          : (delta_is_bf16 ? FN<float, float, __nv_bfloat16>(__VA_ARGS__)                     \
+                                           : FN<float, float, float>(__VA_ARGS__))))
+  return LCBI_LN_DISPATCH3(add_fwd_typed, x, delta, xsum, gamma, beta, y, mean, rstd, rows, C, eps, stream);
+}
+
+int add_layer_norm_bwd_launch(const void* dy, int y_is_bf16, const void* dres, const void* xsum, int x_is_bf16,
+                              const float* gamma, const float* mean, const float* rstd, void* dx, void* ddelta,
+                              int delta_is_bf16, float* dgamma, float* dbeta, float* workspace, size_t workspace_bytes,
+                              int64_t rows, int C, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0) return LCBI_ERR_BAD_ARG;
+  if (C % 4 != 0 || C < 128) return LCBI_ERR_UNSUPPORTED;
+  if (!aligned16(dy) || !aligned16(xsum) || !aligned16(dx) || (dres && !aligned16(dres)) ||
+      (ddelta && !aligned16(ddelta)) || (gamma && !aligned16(gamma)))
+    return LCBI_ERR_BAD_ARG;
+  int rc = LCBI_LN_DISPATCH3(add_bwd_dx_typed, dy, xsum, gamma, mean, rstd, dx, dres, ddelta, rows, C, stream);
+#undef LCBI_LN_DISPATCH3
+  if (rc != LCBI_OK) return rc;
+  if (dgamma != nullptr || dbeta != nullptr)   // parameter gradients: the plain path with dx skipped
+    return layer_norm_bwd_launch(dy, y_is_bf16, xsum, x_is_bf16, gamma, mean, rstd, nullptr, dgamma, dbeta, workspace,
+                                 workspace_bytes, rows, C, stream);
+  return LCBI_OK;
 }
 
 int bias_grad_launch(const void* dy, int dy_is_bf16, float* dbias, float* workspace, size_t workspace_bytes,

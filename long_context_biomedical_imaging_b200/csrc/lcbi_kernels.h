@@ -102,6 +102,13 @@ int layer_norm_bwd_launch(const void* dy, int dy_is_bf16, const void* x, int x_i
                           const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                           float* workspace, size_t workspace_bytes, int64_t rows, int C, cudaStream_t stream);
 
+int add_layer_norm_fwd_launch(const void* x, int x_is_bf16, const void* delta, int delta_is_bf16, void* xsum,
+                              const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean, float* rstd,
+                              int64_t rows, int C, float eps, cudaStream_t stream);
+int add_layer_norm_bwd_launch(const void* dy, int y_is_bf16, const void* dres, const void* xsum, int x_is_bf16,
+                              const float* gamma, const float* mean, const float* rstd, void* dx, void* ddelta,
+                              int delta_is_bf16, float* dgamma, float* dbeta, float* workspace, size_t workspace_bytes,
+                              int64_t rows, int C, cudaStream_t stream);
 int bias_grad_launch(const void* dy, int dy_is_bf16, float* dbias, float* workspace, size_t workspace_bytes,
                      int64_t rows, int C, cudaStream_t stream);
 

@@ -204,11 +204,89 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
         out_dtype = torch.bfloat16 if amp_bf16 else x.dtype
     if x.shape[-1] % 4 != 0:
         raise ValueError("layer_norm needs a channel count that is a multiple of 4")
+    if x.numel() == 0:      # no rows: nothing to launch (an empty batch shard)
+        return torch.nn.functional.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps).to(out_dtype)
     if weight is not None and (weight.dtype != torch.float32 or not weight.is_contiguous()):
         weight = weight.float().contiguous()
     if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
         bias = bias.float().contiguous()
     return _LayerNorm.apply(x, weight, bias, float(eps), out_dtype)
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """(x, delta) -> (xsum = x + delta in x's dtype, y = LayerNorm(xsum) in `out_dtype`): the residual add of an encoder
+    block fused into the LayerNorm that follows it (lcbi_add_layer_norm_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, delta, weight, bias, eps, out_dtype):
+        x, delta = x.contiguous(), delta.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        xsum = torch.empty_like(x)
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rc = _lib.load().lcbi_add_layer_norm_fwd(_p(x), _is_bf16(x), _p(delta), _is_bf16(delta), _p(xsum),
+                                                 _p(weight) if weight is not None else None,
+                                                 _p(bias) if bias is not None else None, _p(y), _is_bf16(y), _p(mean),
+                                                 _p(rstd), rows, C, float(eps), _stream())
+        _lib.check(rc, "lcbi_add_layer_norm_fwd")
+        ctx.save_for_backward(xsum, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        ctx.delta_dtype = delta.dtype
+        ctx.y_dtype = out_dtype
+        return xsum, y
+
+    @staticmethod
+    def backward(ctx, dxsum, dy):
+        xsum, weight, mean, rstd = ctx.saved_tensors
+        C = xsum.shape[-1]
+        rows = xsum.numel() // C
+        if dy is None:
+            dy = torch.zeros(xsum.shape, dtype=ctx.y_dtype, device=xsum.device)
+        dy = dy.contiguous()
+        if dxsum is not None:
+            dxsum = dxsum.contiguous()
+        need_w = weight is not None and ctx.needs_input_grad[2]
+        need_b = ctx.has_bias and ctx.needs_input_grad[3]
+        dx = torch.empty_like(xsum)
+        dd = torch.empty(xsum.shape, dtype=ctx.delta_dtype, device=xsum.device) if ctx.needs_input_grad[1] else None
+        dw = torch.empty((C,), dtype=torch.float32, device=xsum.device) if need_w else None
+        db = torch.empty((C,), dtype=torch.float32, device=xsum.device) if need_b else None
+        lib = _lib.load()
+        ws, ws_bytes = None, 0
+        if need_w or need_b:
+            ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xsum.device)
+        rc = lib.lcbi_add_layer_norm_bwd(_p(dy), _is_bf16(dy), _p(dxsum) if dxsum is not None else None, _p(xsum),
+                                         _is_bf16(xsum), _p(weight) if weight is not None else None, _p(mean), _p(rstd),
+                                         _p(dx), _p(dd) if dd is not None else None,
+                                         1 if ctx.delta_dtype == torch.bfloat16 else 0, _p(dw) if need_w else None,
+                                         _p(db) if need_b else None, _p(ws) if ws is not None else None, ws_bytes, rows,
+                                         C, _stream())
+        _lib.check(rc, "lcbi_add_layer_norm_bwd")
+        return (dx if ctx.needs_input_grad[0] else None), dd, dw, db, None, None
+
+
+def add_layer_norm(x, delta, weight, bias, eps=1e-5, out_dtype=None):
+    """`x = x + delta; y = LayerNorm(x)` of a pre-norm block (reference backbone_vit.py:261-262 followed by the next
+    norm) as one pass. Returns (x + delta, y). Falls back to the two separate steps for rows of < 128 channels or dtype
+    combinations where torch's add would promote away from x's dtype."""
+    _require_cuda(x, delta)
+    fusable = (x.dtype in (torch.float32, torch.bfloat16) and delta.dtype in (torch.float32, torch.bfloat16) and
+               torch.promote_types(x.dtype, delta.dtype) == x.dtype and x.shape == delta.shape and
+               x.shape[-1] % 4 == 0 and x.shape[-1] >= 128 and x.numel() > 0)
+    if not fusable:
+        xsum = x + delta
+        return xsum, layer_norm(xsum, weight, bias, eps, out_dtype)
+    if out_dtype is None:
+        amp_bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        out_dtype = torch.bfloat16 if amp_bf16 else x.dtype
+    if weight is not None and (weight.dtype != torch.float32 or not weight.is_contiguous()):
+        weight = weight.float().contiguous()
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        bias = bias.float().contiguous()
+    return _AddLayerNorm.apply(x, delta, weight, bias, float(eps), out_dtype)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -220,6 +298,8 @@ def bias_grad(dy):
     dy = dy.contiguous()
     C = dy.shape[-1]
     rows = dy.numel() // C
+    if rows == 0:
+        return torch.zeros((C,), dtype=torch.float32, device=dy.device)
     lib = _lib.load()
     out = torch.empty((C,), dtype=torch.float32, device=dy.device)
     ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)

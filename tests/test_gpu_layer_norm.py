@@ -65,6 +65,20 @@ def test_layer_norm_rejects_what_the_kernel_does_not_take():
         ops.layer_norm(torch.randn(4, 6, device="cuda"), None, None)
 
 
+def test_empty_rows_are_not_an_error():
+    from long_context_biomedical_imaging_b200 import ops
+
+    x = torch.zeros(0, 96, device="cuda", requires_grad=True)
+    w = torch.ones(96, device="cuda", requires_grad=True)
+    b = torch.zeros(96, device="cuda", requires_grad=True)
+    y = ops.layer_norm(x, w, b)
+    assert y.shape == (0, 96)
+    z = ops.linear(y, torch.randn(8, 96, device="cuda", requires_grad=True), torch.zeros(8, device="cuda", requires_grad=True))
+    z.sum().backward()
+    assert x.grad.shape == (0, 96) and float(w.grad.abs().max()) == 0.0
+    assert float(ops.bias_grad(torch.zeros(0, 8, device="cuda")).abs().max()) == 0.0
+
+
 def test_layer_norm_under_autocast_feeds_the_linear_in_bf16_and_matches_torch():
     """Inside bf16 autocast the op emits bf16 — the rounding torch's autocast applies to its fp32 LayerNorm output in
     front of a Linear — so block-level results agree with nn.LayerNorm -> nn.Linear to bf16 rounding."""
@@ -152,3 +166,68 @@ def test_bias_grad_full_size():
         want = dy.double().sum(0)
         assert max_rel(got.double().cpu(), want.cpu()) < 1e-5
         assert torch.equal(got, ops.bias_grad(dy))   # deterministic
+
+
+@pytest.mark.parametrize("x_dtype,d_dtype,out_dtype", [(torch.float32, torch.bfloat16, torch.bfloat16),
+                                                       (torch.float32, torch.float32, torch.float32),
+                                                       (torch.bfloat16, torch.bfloat16, torch.bfloat16),
+                                                       (torch.float32, torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("rows_shape,C", [((2, 197), 128), ((3, 50), 192), ((1, 1728), 768), ((70,), 1536), ((40,), 96)])
+def test_fused_residual_add_layer_norm_vs_oracle(rows_shape, C, x_dtype, d_dtype, out_dtype):
+    """(x, delta) -> (x + delta, LayerNorm(x + delta)) — the residual add of a block fused into the norm that follows
+    (reference backbone_vit.py:261-262). Both outputs feed the loss, as in the encoder (hidden state + next branch).
+    C = 96 takes the unfused fallback (narrow rows) and must agree all the same."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(7)
+    x = (torch.randn(*rows_shape, C) * 1.5 + 0.2).to(x_dtype)
+    d = torch.randn(*rows_shape, C).to(d_dtype)
+    w, b = 1 + 0.3 * torch.randn(C), 0.3 * torch.randn(C)
+    g_sum = torch.randn(*rows_shape, C).to(x_dtype)
+    g_y = torch.randn(*rows_shape, C).to(out_dtype)
+
+    xr, dr, wr, br = (t.double().requires_grad_(True) for t in (x, d, w, b))
+    # value rounded like the stored sum, gradient of the plain add
+    sum_r = (xr + dr).detach().to(x_dtype).double() + ((xr + dr) - (xr + dr).detach())
+    y_r = ao.layer_norm_rows(sum_r, wr, br, 1e-5)
+    ref = torch.autograd.grad((sum_r, y_r), (xr, dr, wr, br), (g_sum.double(), g_y.double()))
+
+    xd, dd = x.cuda().requires_grad_(True), d.cuda().requires_grad_(True)
+    wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    xsum, y = ops.add_layer_norm(xd, dd, wd, bd, 1e-5, out_dtype=out_dtype)
+    assert xsum.dtype == x_dtype and y.dtype == out_dtype
+    got = torch.autograd.grad((xsum, y), (xd, dd, wd, bd), (g_sum.cuda(), g_y.cuda()))
+    exact = x_dtype == torch.float32 and d_dtype == torch.float32 and out_dtype == torch.float32
+    tol = 1e-5 if exact else 1e-2
+    assert torch.equal(xsum.detach().cpu(), (x.cuda() + d.cuda()).to(x_dtype).cpu())      # the add itself is bit-exact
+    assert max_rel(y.detach().float().cpu(), y_r.detach()) < tol
+    assert got[0].dtype == x_dtype and got[1].dtype == d_dtype
+    for a, r, name in zip(got, ref, ("dx", "ddelta", "dgamma", "dbeta")):
+        assert max_rel(a.float().cpu(), r) < tol, (name, max_rel(a.float().cpu(), r))
+
+
+def test_vit_block_and_encoder_agree_between_fused_and_per_block_paths():
+    """ViT_with_alt_ops.forward folds every residual add into the following norm across block boundaries; calling the
+    blocks one by one (TransformerBlock.forward, the per-block seam) must give the same hidden states."""
+    import types
+
+    from long_context_biomedical_imaging_b200.backbone_vit import custom_ViT
+
+    cfg = types.SimpleNamespace(ViT=types.SimpleNamespace(size="custom", hidden_size=192, mlp_dim=384, num_layers=3,
+                                                          num_heads=3, patch_size=[1, 8, 8], use_hyena=False,
+                                                          use_mamba=False), time=1, height=32, width=48, task_type="seg")
+    model, _ = custom_ViT(cfg, 1)
+    ao.fill_parameters_(model, 13)
+    model = model.cuda()
+    x = torch.randn(2, 1, 1, 32, 48, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = model(x)
+        t = model.patch_embedding(x.squeeze(2))
+        per_block = []
+        for blk in model.blocks:
+            t = blk(t)
+            per_block.append(t)
+    assert len(outs) == 1 + 3 + 1
+    for got, want in zip(outs[1:-1], per_block):
+        assert got.dtype == want.dtype
+        assert max_rel(got.detach().float().cpu(), want.detach().float().cpu()) < 1e-2
