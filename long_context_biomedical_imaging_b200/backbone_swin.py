@@ -378,7 +378,7 @@ class SwinTransformer_with_alt_ops(nn.Module):
         if self.spatial_dims == 2:
             x = x.squeeze(2)
         hidden_states_out = [x]
-        out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() and
+        out_dtype = torch.bfloat16 if (torch.is_autocast_enabled("cuda") and
                                        torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float32
         t = self.pos_drop(self.patch_embed(x, out_dtype))          # channel-last token grid
         hidden_states_out.append(self._out(t, normalize))

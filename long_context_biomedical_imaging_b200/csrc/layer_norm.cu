@@ -585,7 +585,7 @@ int bias_grad_launch(const void* dy, int dy_is_bf16, float* dbias, float* worksp
 int layer_norm_fwd_launch(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int y_is_bf16,
                           float* mean, float* rstd, int64_t rows, int C, float eps, cudaStream_t stream) {
   if (rows <= 0 || C <= 0 || !(eps >= 0.f)) return LCBI_ERR_BAD_ARG;
-  if (C % 4 != 0 || rows > (int64_t(1) << 31) * kWarpsPerCta) return LCBI_ERR_UNSUPPORTED;
+  if (C % 4 != 0 || rows >= (int64_t(1) << 31) * kWarpsPerCta) return LCBI_ERR_UNSUPPORTED;
   // rows of bf16 start on 8-byte boundaries when C % 4 == 0; the base pointers must be 16-byte aligned
   if (!aligned16(x) || !aligned16(y) || (gamma && !aligned16(gamma)) || (beta && !aligned16(beta))) return LCBI_ERR_BAD_ARG;
   if (x_is_bf16) {
@@ -600,7 +600,7 @@ int layer_norm_bwd_launch(const void* dy, int dy_is_bf16, const void* x, int x_i
                           const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                           float* workspace, size_t workspace_bytes, int64_t rows, int C, cudaStream_t stream) {
   if (rows <= 0 || C <= 0) return LCBI_ERR_BAD_ARG;
-  if (C % 4 != 0 || rows > (int64_t(1) << 31) * kWarpsPerCta) return LCBI_ERR_UNSUPPORTED;
+  if (C % 4 != 0 || rows >= (int64_t(1) << 31) * kWarpsPerCta) return LCBI_ERR_UNSUPPORTED;
   if (!aligned16(dy) || !aligned16(x) || (dx && !aligned16(dx)) || (gamma && !aligned16(gamma))) return LCBI_ERR_BAD_ARG;
   if ((dgamma != nullptr || dbeta != nullptr) &&
       (workspace == nullptr || !aligned16(workspace) || workspace_bytes < layer_norm_bwd_workspace_bytes(rows, C)))

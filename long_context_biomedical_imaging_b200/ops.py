@@ -200,7 +200,7 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     if out_dtype is None:
-        amp_bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        amp_bf16 = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
         out_dtype = torch.bfloat16 if amp_bf16 else x.dtype
     if x.shape[-1] % 4 != 0:
         raise ValueError("layer_norm needs a channel count that is a multiple of 4")
@@ -280,7 +280,7 @@ def add_layer_norm(x, delta, weight, bias, eps=1e-5, out_dtype=None):
         xsum = x + delta
         return xsum, layer_norm(xsum, weight, bias, eps, out_dtype)
     if out_dtype is None:
-        amp_bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        amp_bf16 = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
         out_dtype = torch.bfloat16 if amp_bf16 else x.dtype
     if weight is not None and (weight.dtype != torch.float32 or not weight.is_contiguous()):
         weight = weight.float().contiguous()
@@ -343,8 +343,8 @@ def linear(x, weight, bias):
     the MLP: reference backbone_vit.py:167,202,249; backbone_swin.py:309-311,433)."""
     if bias is None or not x.is_cuda or bias.shape[0] % 4 != 0 or x.dtype not in (torch.float32, torch.bfloat16):
         return torch.nn.functional.linear(x, weight, bias)
-    if torch.is_autocast_enabled():
-        compute_dtype = torch.get_autocast_gpu_dtype()
+    if torch.is_autocast_enabled("cuda"):
+        compute_dtype = torch.get_autocast_dtype("cuda")
         if compute_dtype != torch.bfloat16:
             return torch.nn.functional.linear(x, weight, bias)
     else:

@@ -1,4 +1,6 @@
-"""GPU parity of the LayerNorm kernels (lcbi_layer_norm_fwd / _bwd through ops.layer_norm) against the CPU oracle's
+"""GPU parity of the kernels around the attention core — LayerNorm (lcbi_layer_norm_fwd / _bwd through ops.layer_norm),
+the residual add fused into it (lcbi_add_layer_norm_*, ops.add_layer_norm) and the bias gradient of the projections
+(lcbi_bias_grad behind ops.linear). LayerNorm is checked against the CPU oracle's
 written-out LayerNorm (oracle.attention_oracle.layer_norm_rows, pinned against torch.nn.LayerNorm in
 tests/test_oracle_golden.py): the norm1 / norm2 of the encoder blocks (reference backbone_vit.py:260-263,
 backbone_swin.py:437,489).
