@@ -370,7 +370,7 @@ class SwinTransformer_with_alt_ops(nn.Module):
     def _out(self, x_cl, normalize):
         if not normalize:
             return self._channel_first(x_cl)
-        if x_cl.is_cuda and x_cl.shape[-1] % 4 == 0:   # affine-free; fp32 out like the reference's autocast layer_norm
+        if x_cl.shape[-1] % 4 == 0:   # affine-free; fp32 out like the reference's autocast layer_norm
             return self._channel_first(ops.layer_norm(x_cl, None, None, 1e-5, out_dtype=torch.float32))
         return self._channel_first(F.layer_norm(x_cl, [x_cl.shape[-1]]))
 

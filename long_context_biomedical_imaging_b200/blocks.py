@@ -35,10 +35,11 @@ def apply_layer_norm(norm, x, out_dtype=None):
     statistics, output written in the dtype the next Linear consumes). The module keeps its parameters (state_dict
     keys norm1 / norm2 / norm as in the reference: backbone_vit.py:249-258, backbone_swin.py:419-433); any other
     norm_layer, or a channel count the kernel does not take, runs as the module itself."""
-    if (type(norm) is nn.LayerNorm and x.is_cuda and len(norm.normalized_shape) == 1 and
+    ops._require_cuda(x)      # like every operator of this package: no CPU path
+    if (type(norm) is nn.LayerNorm and len(norm.normalized_shape) == 1 and
             norm.normalized_shape[0] == x.shape[-1] and x.shape[-1] % 4 == 0):
         return ops.layer_norm(x, norm.weight, norm.bias, norm.eps, out_dtype)
-    y = norm(x)
+    y = norm(x)               # another norm_layer class or an odd channel count: the (CUDA) module itself
     return y if out_dtype is None else y.to(out_dtype)
 
 
@@ -47,7 +48,8 @@ def apply_add_layer_norm(norm, x, delta, out_dtype=None):
     sum (reference backbone_vit.py:261-262). `delta=None` means there is nothing to add yet (first block)."""
     if delta is None:
         return x, apply_layer_norm(norm, x, out_dtype)
-    if (type(norm) is nn.LayerNorm and x.is_cuda and len(norm.normalized_shape) == 1 and
+    ops._require_cuda(x, delta)
+    if (type(norm) is nn.LayerNorm and len(norm.normalized_shape) == 1 and
             norm.normalized_shape[0] == x.shape[-1]):
         return ops.add_layer_norm(x, delta, norm.weight, norm.bias, norm.eps, out_dtype)
     x = x + delta

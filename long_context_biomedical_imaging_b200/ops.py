@@ -14,7 +14,7 @@ from . import _lib
 
 def _require_cuda(*tensors):
     for t in tensors:
-        if not t.is_cuda:
+        if t is not None and not t.is_cuda:
             raise RuntimeError("lcbi_b200 operators need CUDA tensors: there is no CPU fallback for the attention hot path")
 
 
@@ -341,8 +341,9 @@ class _LinearBias(torch.autograd.Function):
 def linear(x, weight, bias):
     """Drop-in for `nn.Linear(...)(x)` with a bias on CUDA tensors (the projections around the attention kernels and
     the MLP: reference backbone_vit.py:167,202,249; backbone_swin.py:309-311,433)."""
-    if bias is None or not x.is_cuda or bias.shape[0] % 4 != 0 or x.dtype not in (torch.float32, torch.bfloat16):
-        return torch.nn.functional.linear(x, weight, bias)
+    _require_cuda(x)
+    if bias is None or bias.shape[0] % 4 != 0 or x.dtype not in (torch.float32, torch.bfloat16):
+        return torch.nn.functional.linear(x, weight, bias)      # nothing of ours to run: plain cuBLAS Linear
     if torch.is_autocast_enabled("cuda"):
         compute_dtype = torch.get_autocast_dtype("cuda")
         if compute_dtype != torch.bfloat16:

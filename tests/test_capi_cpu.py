@@ -51,6 +51,17 @@ def test_ops_refuse_cpu_tensors():
         ops.dense_attention_qkv(torch.randn(1, 8, 192), 1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.patch_embed(torch.randn(1, 1, 8, 8), torch.randn(4, 1, 2, 2), torch.randn(4), None, (4, 4))
+    from long_context_biomedical_imaging_b200.blocks import apply_add_layer_norm, apply_layer_norm
+
+    ln = torch.nn.LayerNorm(8)
+    for call in (lambda: ops.layer_norm(torch.randn(4, 8), None, None),
+                 lambda: ops.add_layer_norm(torch.randn(4, 256), torch.randn(4, 256), None, None),
+                 lambda: ops.linear(torch.randn(4, 8), torch.randn(8, 8), torch.randn(8)),
+                 lambda: ops.bias_grad(torch.randn(4, 8)),
+                 lambda: apply_layer_norm(ln, torch.randn(4, 8)),
+                 lambda: apply_add_layer_norm(ln, torch.randn(4, 8), torch.randn(4, 8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
 
 
 def _vit_cfg(**kw):
