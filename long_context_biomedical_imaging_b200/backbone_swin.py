@@ -23,7 +23,6 @@ from __future__ import annotations
 import itertools
 from collections.abc import Sequence
 
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

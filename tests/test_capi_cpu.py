@@ -1,6 +1,5 @@
 """CPU: the C-ABI library builds, loads, and exports every symbol include/lcbi_b200.h declares; host logic of
 the module mirrors (factories, state_dict layout, error behaviour) that needs no GPU."""
-import ctypes
 import os
 import re
 import types

@@ -1,4 +1,6 @@
-import os, sys, torch
+import sys
+
+import torch
 sys.path.insert(0, "/root/repo")
 from long_context_biomedical_imaging_b200 import ops
 def t(B, N, kind="fwd"):
