@@ -84,6 +84,14 @@ constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTme
 #ifndef LCBI_BWD_CHUNKED
 #define LCBI_BWD_CHUNKED 0
 #endif
+// 1 (experimental, not yet run on hardware): 32-query pipeline steps with FOUR 32-column S^T / dP^T buffers. Warps 0-3
+// take the even 32-query steps and warps 4-7 the odd ones, each group double-buffered on its own pair of buffers
+// (buffer = 2 * group + (step / 2) % 2), so the two warps of an SM sub-partition run half a step apart without giving
+// up the overlap of a group's compute with the tensor core's work on its other buffer. The Q / dO ring, the dS^T smem
+// tiles, dQ per 128 queries, the epilogue and the drain warps are unchanged; a ring stage (64 queries) serves two steps.
+#ifndef LCBI_BWD_Q32
+#define LCBI_BWD_Q32 0
+#endif
 // > 0: exponentials and the products / packs that consume them are interleaved pair by pair, LAG pairs apart (see the loop)
 #ifndef LCBI_BWD_INTERLEAVE
 #define LCBI_BWD_INTERLEAVE 0
@@ -114,7 +122,7 @@ struct __align__(1024) BwdSmem {
   uint8_t aug_zeros[2 * kAugBytes];       // second k-half of every row-term tile (placed after them: LBO > 0)
   uint64_t k_full[2], v_full;
   uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
-  uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full, dkv_drained;
+  uint64_t sdp_full[LCBI_BWD_Q32 ? 4 : 2], pds_full[LCBI_BWD_Q32 ? 4 : 2], kvt_full, dq_full, dq_empty, dkv_full, dkv_drained;
   uint32_t tmem_base;
 };
 
@@ -310,9 +318,9 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_init(&sm.do_full[s], 1);
       mbar_init(&sm.do_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < (LCBI_BWD_Q32 ? 4 : 2); ++b) {
       mbar_init(&sm.sdp_full[b], 1);
-      mbar_init(&sm.pds_full[b], LCBI_BWD_SPLIT_STEPS ? 4 : 8);   // one arrive per compute warp working on the buffer
+      mbar_init(&sm.pds_full[b], (LCBI_BWD_SPLIT_STEPS || LCBI_BWD_Q32) ? 4 : 8);   // one arrive per compute warp working on the buffer
     }
     mbar_init(&sm.kvt_full, 8);
     mbar_init(&sm.dq_full, 1);
@@ -427,6 +435,71 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         umma_commit(&sm.sdp_full[b]);
       };
 
+#if LCBI_BWD_Q32
+      // 32-query steps: global step counter g32 = it * n32 + s; ring stage of a step = its 64-query index (g32 >> 1);
+      // S^T / dP^T buffer j = 2 * (g32 & 1) + ((g32 >> 1) & 1) at columns 32 j, used every fourth step (phase g32 >> 2)
+      constexpr uint32_t idesc_nt32 = make_idesc_bf16(kTile, 32, 0, 0);
+      const int n32 = 2 * n_steps;
+      auto buf_of = [](int g32) { return 2 * (g32 & 1) + ((g32 >> 1) & 1); };
+      auto issue_sdp32 = [&](int g32) {
+        const int gst = g32 >> 1, st = gst % kQStages, h = g32 & 1, j = buf_of(g32);
+        // rows 32 h .. 32 h + 31 of the stage's tiles: 4 KB into the swizzled Q / dO tile, 512 B into the row-term tiles
+        const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes + h * 4096), ddo_s = desc_advance(d_do0, st * kStepBytes + h * 4096);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)
+          umma_ts(tmem + kTmemS + j * 32, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt32, kk > 0 ? 1u : 0u);
+        umma_ss(tmem + kTmemS + j * 32, d_ones, aug_stage(d_lse0, st) + (h * 512 >> 4), idesc_nt32, 1u);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)
+          umma_ts(tmem + kTmemDP + j * 32, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt32, kk > 0 ? 1u : 0u);
+        umma_ss(tmem + kTmemDP + j * 32, d_ones, aug_stage(d_d0, st) + (h * 512 >> 4), idesc_nt32, 1u);
+        umma_commit(&sm.sdp_full[j]);
+      };
+      int it = 0;
+      for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+        const int g0 = it * n32, gi0 = it * n_tiles;
+        const uint64_t d_k = desc_advance(d_k0, (it & 1) * kTileBytes);
+        mbar_wait(&sm.kvt_full, it & 1);
+        for (int s = 0; s < 4; ++s) {          // n32 >= 4: Nq_pad is a multiple of 128
+          if ((s & 1) == 0) wait_sdp_operands((g0 + s) >> 1);
+          tc_fence_after();
+          issue_sdp32(g0 + s);
+        }
+        for (int s = 0; s < n32; ++s) {
+          const int g32 = g0 + s, gst = g32 >> 1, st = gst % kQStages, h = g32 & 1, j = buf_of(g32), gi = gi0 + (s >> 2);
+          if (s + 4 < n32 && (s & 1) == 0) wait_sdp_operands((g32 + 4) >> 1);
+          if ((s & 3) == 3) mbar_wait(&sm.dq_empty, (gi & 1) ^ 1);
+          if (s == 0 && it > 0) mbar_wait(&sm.dkv_drained, (it - 1) & 1);
+          mbar_wait(&sm.pds_full[j], (g32 >> 2) & 1);
+          tc_fence_after();
+          const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
+          // dV += P^T dO, dK += dS^T Q over this step's 32 queries: two k-steps of 16 (8 packed columns each); the B
+          // operand rows are queries 32 h + 16 kk of the 64-query stage tile
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_ts(tmem + kTmemDV, tmem + kTmemS + j * 32 + kk * 8, desc_advance(ddo_s, (2 * h + kk) * 2048), idesc_kmn,
+                    (s > 0 || kk > 0) ? 1u : 0u);
+          if (h) umma_commit(&sm.do_empty[st]);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_ts(tmem + kTmemDK, tmem + kTmemDP + j * 32 + kk * 8, desc_advance(dq_s, (2 * h + kk) * 2048), idesc_kmn,
+                    (s > 0 || kk > 0) ? 1u : 0u);
+          if (h) umma_commit(&sm.q_empty[st]);
+          if (s + 4 < n32) issue_sdp32(g32 + 4);
+          if ((s & 3) == 3) {
+            const uint64_t dds_mn = desc_advance(d_ds_mn0, (gi & 1) * 2 * kTileBytes);
+#pragma unroll
+            for (int kk = 0; kk < kTile / 16; ++kk)
+              umma_ss(tmem + kTmemDQ, desc_advance(dds_mn, kk * 2048), desc_advance(d_k, kk * 2048), idesc_mnmn,
+                      kk > 0 ? 1u : 0u);
+            umma_commit(&sm.dq_full);
+          }
+        }
+        umma_commit(&sm.dkv_full);
+      }
+      (void)idesc_nt;
+      (void)issue_sdp;
+#else
       int it = 0;
       for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
         const int gs0 = it * n_steps, gi0 = it * n_tiles;
@@ -481,6 +554,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         umma_commit(&sm.dkv_full);
       }
+#endif
     }
   } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ dQ drain (warps 8-11)
@@ -590,7 +664,7 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     bool store_pending = false;                 // the previous item's dV/dK store may still be reading its staging tiles
     auto finish_store = [&]() {
       if (store_issuer) tma_store_wait_read<0>();
-#if LCBI_BWD_SPLIT_STEPS
+#if LCBI_BWD_SPLIT_STEPS && !LCBI_BWD_Q32
       if (!p.accumulate_dkv) named_bar_sync(5 + hh, 128);   // the staging atom is this group's own
       else
 #endif
@@ -626,7 +700,50 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       LCBI_ITEM_T(0);
       if (it == 0) copy_kv_to_tmem(0);           // later items: done at the end of the previous item's last step
 
-#if LCBI_BWD_SPLIT_STEPS
+#if LCBI_BWD_Q32
+      // 32-query steps (see LCBI_BWD_Q32 at the top): this group's steps are s = hh, hh + 2, ...; all 32 columns of the
+      // step's buffer belong to this thread's key row
+      const int n32 = 2 * n_steps, g0 = it * n32;
+      for (int s = hh; s < n32; s += 2) {
+        const int g32 = g0 + s, j = 2 * hh + ((g32 >> 1) & 1), gi = gi0 + (s >> 2);
+        // the previous item's dV / dK staging tiles are the two atoms of this item's second 128-query tile, each of
+        // which both groups write (steps 4, 5 / 6, 7): both stores must have been read before either group gets there
+        if (store_pending && (p.accumulate_dkv || s == 4 + hh)) finish_store();
+        mbar_wait(&sm.sdp_full[j], (g32 >> 2) & 1);
+        tc_fence_after();
+        uint32_t sv[32], dpv[32];
+        tmem_ld_x32(tmem + lane_sel + kTmemS + j * 32, sv);
+        tmem_ld_x32(tmem + lane_sel + kTmemDP + j * 32, dpv);
+        tmem_ld_wait();
+        uint32_t pk[16], dsk[16];
+        // dS^T smem atom = the 64-query half of the 128-query tile this step lies in; 16-byte chunks 4 h .. 4 h + 3
+        uint8_t* ds_atom = sm.ds[gi & 1] + ((s >> 1) & 1) * kTileBytes;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
+                       "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
+        tmem_st_x16(tmem + lane_sel + kTmemS + j * 32, pk);
+        tmem_st_x16(tmem + lane_sel + kTmemDP + j * 32, dsk);
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.pds_full[j]);
+      }
+      // all S^T / dP^T GEMMs of the item must have retired before K / V of the next item replace this item's in TMEM:
+      // this thread consumed its own group's; the other group's last two steps are waited for here (those barriers
+      // cannot complete another phase before this thread has copied its rows)
+      for (int back = 0; back < 2; ++back) {
+        const int s_o = n32 - 1 - hh - 2 * back, g_o = g0 + s_o;      // steps of the other parity: n32 - 1 - hh, minus 2
+        mbar_wait(&sm.sdp_full[2 * (1 - hh) + ((g_o >> 1) & 1)], (g_o >> 2) & 1);
+      }
+#elif LCBI_BWD_SPLIT_STEPS
       // Warps 0-3 take the even steps, warps 4-7 the odd ones, each all 64 query columns of its step (two passes of 32).
       // A group then always works on the same S^T / dP^T buffer (b == hh), and the two warps that share an SM
       // sub-partition run half a step apart: one is in its MUFU burst while the other packs, stores and fences.
