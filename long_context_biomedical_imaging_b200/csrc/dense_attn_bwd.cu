@@ -84,7 +84,8 @@ constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTme
 #ifndef LCBI_BWD_CHUNKED
 #define LCBI_BWD_CHUNKED 0
 #endif
-// 1 (experimental, not yet run on hardware): 32-query pipeline steps with FOUR 32-column S^T / dP^T buffers. Warps 0-3
+// 1 (experiment; parity-green on a B200 but slower, 0.610 vs 0.48 ms at cfg3: twice the hand-offs and row-term MMAs per
+// query): 32-query pipeline steps with FOUR 32-column S^T / dP^T buffers. Warps 0-3
 // take the even 32-query steps and warps 4-7 the odd ones, each group double-buffered on its own pair of buffers
 // (buffer = 2 * group + (step / 2) % 2), so the two warps of an SM sub-partition run half a step apart without giving
 // up the overlap of a group's compute with the tensor core's work on its other buffer. The Q / dO ring, the dS^T smem
