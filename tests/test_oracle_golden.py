@@ -129,3 +129,61 @@ def test_layer_norm_restatement_matches_the_reference_module_class():
         assert max_rel(out.detach().numpy(), ref.detach().numpy()) < 1e-12
         for a, r in zip(grads, ref_grads):
             assert max_rel(a.numpy(), r.numpy()) < 1e-11
+
+
+def _partition_by_copies(grid, window, shift):
+    """The reference's data movement spelled out with array copies (backbone_swin.py:441-468, :135-165): clamp the
+    window, zero-pad the far ends, roll by -shift, cut raster-ordered windows. Applied to an arange token grid it gives
+    the gather map; applied to the region-label image of compute_mask (:604-624) it gives the region ids."""
+    win, sh = wm.resolve_window(grid, window, shift)
+    K = len(grid)
+    pads = [(0, (-g) % w) for g, w in zip(grid, win)]
+
+    def cut(img):
+        shape = []
+        for n_k, w in zip(img.shape, win):
+            shape += [n_k // w, w]
+        t = img.reshape(shape)
+        t = t.transpose([2 * k for k in range(K)] + [2 * k + 1 for k in range(K)])
+        return t.reshape(-1, int(np.prod(win)))
+
+    tokens = np.arange(int(np.prod(grid)), dtype=np.int64).reshape(grid)
+    padded = np.pad(tokens, pads, constant_values=-1)
+    rolled = np.roll(padded, [-s for s in sh], axis=tuple(range(K))) if any(sh) else padded
+    gather = cut(rolled)
+
+    labels = np.zeros(padded.shape, dtype=np.int64)
+    cnt = 0
+    import itertools
+    slabs = [(slice(-w), slice(-w, -s), slice(-s, None)) for w, s in zip(win, sh)]
+    for combo in itertools.product(*slabs):
+        labels[combo] = cnt
+        cnt += 1
+    return gather, cut(labels)
+
+
+def test_closed_form_maps_equal_pad_roll_partition_on_random_geometries():
+    """Beyond the 22 golden geometries: the closed forms agree with the copy-based restatement for random 2-D / 3-D
+    grids, windows and shifts (clamped axes, zero shifts on some axes, non-divisible grids)."""
+    from hypothesis import given, settings, strategies as st
+
+    @st.composite
+    def geometry(draw):
+        k = draw(st.sampled_from([2, 3]))
+        grid = tuple(draw(st.integers(1, 11 if k == 3 else 20)) for _ in range(k))
+        window = tuple(draw(st.integers(1, 7)) for _ in range(k))
+        shift = tuple(draw(st.integers(0, w - 1)) if draw(st.booleans()) else 0 for w in window)
+        return grid, window, shift
+
+    @settings(max_examples=150, deadline=None)
+    @given(geometry())
+    def check(geo):
+        grid, window, shift = geo
+        gather, labels = _partition_by_copies(grid, window, shift)
+        assert np.array_equal(wm.gather_map(grid, window, shift), gather)
+        ids = wm.region_ids(grid, window, shift)
+        same_ref = labels[:, :, None] == labels[:, None, :]
+        same_ours = ids[:, :, None] == ids[:, None, :]
+        assert np.array_equal(same_ref, same_ours)       # the mask only depends on which slots share a region
+
+    check()
