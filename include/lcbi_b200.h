@@ -38,8 +38,10 @@ int lcbi_version(void);
 
 /* The dense attention kernels are persistent (one or two CTAs per SM for the whole launch). When a communication
  * kernel must run BESIDE them (ring K/V exchange over NCCL on a side stream), it needs SMs of its own: the next
- * launches leave `n` SMs unused (0..64, default 0; process-wide). */
+ * launches ON THE CURRENT DEVICE leave `n` SMs unused (0..64, default 0; one setting per device ordinal).
+ * lcbi_get_reserved_sms() returns the current device's setting so a caller can restore it afterwards. */
 int lcbi_set_reserved_sms(int n);
+int lcbi_get_reserved_sms(void);
 const char* lcbi_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -55,13 +57,27 @@ int lcbi_dense_attn_fwd(const void* q, const void* k, const void* v, void* o, fl
                         int Nk, int head_dim, const int64_t* q_strides, const int64_t* k_strides,
                         const int64_t* v_strides, const int64_t* o_strides, float scale, void* stream);
 
+/* Ring (sequence-parallel) step of the same forward — functionality the reference does not have ("optional
+ * running (m, l, O) in/out for ring steps"). One call per visiting K/V shard; the online-softmax state of every local
+ * query row is carried from call to call instead of being merged afterwards:
+ *   state_o: fp32 (B,Nq,H,d) contiguous un-normalised running output; state_m / state_l: fp32 (B,H,Nq) running max
+ *   (raw score units) and running row sum. first != 0: the incoming state is ignored (first shard). last != 0: the
+ *   result is normalised and written to o (bf16) and lse exactly as lcbi_dense_attn_fwd does, and the state is left
+ *   untouched; otherwise only the state is written back (o, lse, o_strides may be NULL). first && last == a plain call. */
+int lcbi_dense_attn_fwd_state(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq,
+                              int Nk, int head_dim, const int64_t* q_strides, const int64_t* k_strides,
+                              const int64_t* v_strides, const int64_t* o_strides, float scale, float* state_o,
+                              float* state_m, float* state_l, int first, int last, void* stream);
+
 /* Backward of the above (what autograd derives for backbone_vit.py:191-201).
  *   d_o, o: (B,Nq,H,d) bf16 views; dq: (B,Nq,H,d), dk/dv: (B,Nk,H,d) bf16 views.
  *   accumulate_dkv != 0: dk/dv are instead fp32 (B,Nk,H,d) CONTIGUOUS buffers that are accumulated into
  *   (ring sequence-parallel steps); their stride arguments are ignored.
  *   accumulate_dq != 0: likewise dq is an fp32 (B,Nq,H,d) contiguous buffer that is accumulated into.
- *   workspace: at least lcbi_dense_attn_bwd_workspace_bytes() bytes, 128-byte aligned. */
+ *   workspace: at least lcbi_dense_attn_bwd_workspace_bytes() bytes, 128-byte aligned; with accumulate_dq the fp32 dQ
+ *   accumulator inside it is not needed and lcbi_dense_attn_bwd_workspace_bytes_for(..., 1) (row-term tiles only) suffices. */
 size_t lcbi_dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
+size_t lcbi_dense_attn_bwd_workspace_bytes_for(int B, int H, int Nq, int head_dim, int accumulate_dq);
 int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                         const float* lse, void* dq, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
                         const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,

@@ -25,7 +25,11 @@ SIGNATURES = {
     "lcbi_dense_attn_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, c_i64p, c_i64p, c_i64p, c_i64p, ctypes.c_float,
                                            c_vp]),
+    "lcbi_dense_attn_fwd_state": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, c_i64p, c_i64p, c_i64p, c_i64p,
+                                                 ctypes.c_float, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
     "lcbi_dense_attn_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "lcbi_dense_attn_bwd_workspace_bytes_for": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "lcbi_dense_attn_bwd": (ctypes.c_int, [c_vp] * 9 + [ctypes.c_int] * 5 + [c_i64p] * 8 +
                             [ctypes.c_float, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
     "lcbi_attn_merge": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -56,6 +60,7 @@ SIGNATURES = {
                                                ctypes.c_int, c_vp]),
     "lcbi_bias_grad": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int, c_vp]),
     "lcbi_set_reserved_sms": (ctypes.c_int, [ctypes.c_int]),
+    "lcbi_get_reserved_sms": (ctypes.c_int, []),
     "lcbi_window_maps": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_i32p, c_i32p, c_vp]),
 }
 

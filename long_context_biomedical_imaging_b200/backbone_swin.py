@@ -17,6 +17,10 @@ What changes: `forward_part1` is norm1 -> qkv Linear -> ONE fused kernel (window
 QK^T + relative-position bias + shift mask, softmax, PV, scatter back) -> proj Linear. There is no F.pad,
 torch.roll, window_partition, window_reverse, mask tensor or per-forward bias gather; tokens stay channel-last
 between stages and channel-first tensors are exposed as views exactly where the reference returns them.
+
+Window parallelism (new relative to the reference): `window_group=<process group>` (or `config.Swin.window_group`)
+splits the (batch, window) list of every attention block over the ranks of the group (`window_parallel.py`);
+everything token-wise stays replicated, so every rank still returns the full hidden states.
 """
 from __future__ import annotations
 
@@ -29,7 +33,7 @@ import torch.nn.functional as F
 import torch.utils.checkpoint as checkpoint
 from torch.nn import LayerNorm
 
-from . import ops
+from . import ops, window_parallel
 from .blocks import MLPBlock as Mlp
 from .blocks import PatchEmbed, apply_layer_norm
 
@@ -73,6 +77,8 @@ def custom_Swin(config, input_feature_channels):
     model = SwinTransformer_with_alt_ops(use_hyena=config.Swin.use_hyena, use_mamba=config.Swin.use_mamba,
                                          in_chans=input_feature_channels, embed_dim=embed_dim, window_size=window,
                                          patch_size=patch, depths=depths, num_heads=num_heads, spatial_dims=spatial_dims)
+    if getattr(config.Swin, "window_group", None) is not None:
+        model.set_window_group(config.Swin.window_group)
     n = len(depths)
     return model, [embed_dim * 2 ** i for i in range(n)] + [embed_dim * 2 ** n]
 
@@ -171,12 +177,26 @@ class WindowAttention(nn.Module):
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.proj = nn.Linear(dim, dim)
         nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+        self.window_group = None     # process group the block's windows are sharded over (set_window_group)
 
     def forward_grid(self, x, shift_size):
         """x: (B, *grid, C) normed tokens on the un-padded grid -> (B, *grid, C). The whole of the reference's
         pad/roll/partition -> attention -> reverse/roll/crop chain."""
         qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
-        o = ops.window_attention(qkv, self.qkv.bias, self.relative_position_bias_table, x.shape[1:-1],
+        grid = tuple(x.shape[1:-1])
+        group = self.window_group
+        if group is not None:
+            import torch.distributed as dist
+
+            pg = None if group == "world" else group
+            # blocks with fewer windows than ranks (late stages: 27 / 8 windows) stay replicated
+            if (dist.is_available() and dist.is_initialized() and dist.get_world_size(pg) > 1 and
+                    x.shape[0] * window_parallel.count_windows(grid, self.window_size) >= dist.get_world_size(pg)):
+                o = window_parallel.window_attention_sharded(qkv, self.qkv.bias, self.relative_position_bias_table,
+                                                             grid, self.window_size, shift_size, self.num_heads,
+                                                             self.scale, group=pg)
+                return ops.linear(o, self.proj.weight, self.proj.bias)
+        o = ops.window_attention(qkv, self.qkv.bias, self.relative_position_bias_table, grid,
                                  self.window_size, shift_size, self.num_heads, self.scale)
         return ops.linear(o, self.proj.weight, self.proj.bias)
 
@@ -354,6 +374,12 @@ class SwinTransformer_with_alt_ops(nn.Module):
                                      drop=drop_rate, attn_drop=attn_drop_rate, norm_layer=norm_layer, downsample=down,
                                      use_checkpoint=use_checkpoint))
         self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+
+    def set_window_group(self, group):
+        """Shard the windows of every attention block over `group` ("world" = the default group; None = off)."""
+        for m in self.modules():
+            if isinstance(m, WindowAttention):
+                m.window_group = group
 
     @staticmethod
     def _channel_first(x_cl):

@@ -14,6 +14,12 @@ path runs: the attention core is one fused tcgen05 kernel reading q/k/v in place
 output (no rearrange copies, no N x N matrix), and the patch embedding is a fused CUDA kernel
 (conv-as-GEMM + bias + position embedding). LayerNorm / MLP / qkv / out_proj stay torch ops.
 
+Sequence parallelism (new relative to the reference, which has DDP only: trainer/trainer_base.py:94-98): pass
+`sequence_group=<process group>` (or set `config.ViT.sequence_group`) and every rank runs the encoder on its
+contiguous slice of the token sequence — its rows of the image go through the patch embedding with its rows of
+`position_embeddings`, LayerNorm / MLP / qkv / out_proj are token-local, and the attention core becomes ring attention
+over the group (`ring.py`). Hidden states are returned as local slices, or gathered with `gather_outputs=True`.
+
 use_hyena / use_mamba select the reference's alternative mixers, which are outside this package's scope:
 requesting them raises NotImplementedError naming the reference module to use instead.
 """
@@ -24,7 +30,7 @@ from collections.abc import Sequence
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, ring
 from .blocks import MLPBlock, PatchEmbeddingBlock, apply_add_layer_norm, apply_layer_norm
 
 _ALT_MIXER_MSG = ("use_hyena/use_mamba route to the reference's HyenaOperator / MambaVisionMixer "
@@ -62,7 +68,9 @@ def custom_ViT(config, input_feature_channels):
     model = ViT_with_alt_ops(use_hyena=config.ViT.use_hyena, use_mamba=config.ViT.use_mamba,
                              in_channels=input_feature_channels, img_size=input_size, patch_size=patch,
                              hidden_size=hidden_size, mlp_dim=mlp_dim, num_layers=num_layers, num_heads=num_heads,
-                             dropout_rate=0.0, spatial_dims=spatial_dims, classification=config.task_type == "class")
+                             dropout_rate=0.0, spatial_dims=spatial_dims, classification=config.task_type == "class",
+                             sequence_group=getattr(config.ViT, "sequence_group", None),
+                             gather_outputs=getattr(config.ViT, "gather_outputs", True))
     return model, [hidden_size] * 13
 
 
@@ -95,10 +103,14 @@ class SABlock(nn.Module):
         self.att_mat = torch.Tensor()
         self.qkv = nn.Linear(hidden_size, hidden_size * 3, bias=qkv_bias)
         self.out_proj = nn.Linear(hidden_size, hidden_size)
+        self.ring_comm = None      # set by ViT_with_alt_ops when the sequence is sharded over a process group
 
     def forward(self, x):
         qkv = self.qkv(x)                                        # (B, N, 3C), feature = s*C + h*d + j
-        o = ops.dense_attention_qkv(qkv, self.num_heads, self.scale)   # (B, N, C), feature = h*d + j
+        if self.ring_comm is not None:                           # x is this rank's token slice: ring K/V exchange
+            o = ring.ring_attention_qkv(qkv, self.num_heads, self.ring_comm, self.scale)
+        else:
+            o = ops.dense_attention_qkv(qkv, self.num_heads, self.scale)   # (B, N, C), feature = h*d + j
         return ops.linear(o, self.out_proj.weight, self.out_proj.bias)   # cuBLAS GEMMs, fused-kernel bias gradient
 
 
@@ -132,7 +144,7 @@ class ViT_with_alt_ops(nn.Module):
                  num_heads: int = 12, pos_embed: str = "conv", proj_type: str = "conv",
                  pos_embed_type: str = "learnable", classification: bool = False, num_classes: int = 2,
                  dropout_rate: float = 0.0, spatial_dims: int = 3, post_activation="Tanh", qkv_bias: bool = False,
-                 save_attn: bool = False) -> None:
+                 save_attn: bool = False, sequence_group=None, gather_outputs: bool = True) -> None:
         super().__init__()
         if not (0 <= dropout_rate <= 1):
             raise ValueError("dropout_rate should be between 0 and 1.")
@@ -152,12 +164,57 @@ class ViT_with_alt_ops(nn.Module):
         self.norm = nn.LayerNorm(hidden_size)
         if self.classification:
             self.cls_token = nn.Parameter(torch.zeros(1, 1, hidden_size))
+        self.sequence_group = None
+        self.gather_outputs = gather_outputs
+        self._ring_comm = None
+        if sequence_group is not None:
+            self.set_sequence_group(sequence_group)
+
+    def set_sequence_group(self, group, gather_outputs=None):
+        """Shard the token sequence over `group` (None: back to one device per replica). The communicator is created
+        at the first forward (torch.distributed must be initialised by then)."""
+        if group is not None and self.classification:
+            raise NotImplementedError("sequence parallelism with a cls token (task_type 'class') would make the shards "
+                                      "uneven; the long-sequence configurations are dense-prediction encoders")
+        self.sequence_group = group
+        self._ring_comm = None
+        if gather_outputs is not None:
+            self.gather_outputs = gather_outputs
+        if group is None:
+            for blk in self.blocks:
+                blk.attn.ring_comm = None
+
+    def _sequence_comm(self):
+        import torch.distributed as dist
+
+        if self.sequence_group is None or not (dist.is_available() and dist.is_initialized()):
+            return None
+        group = None if self.sequence_group == "world" else self.sequence_group
+        if dist.get_world_size(group) == 1:
+            return None
+        if self._ring_comm is None:
+            self._ring_comm = ring.RingComm(group)
+            for blk in self.blocks:
+                blk.attn.ring_comm = self._ring_comm
+        return self._ring_comm
 
     def forward(self, x):
         if self.spatial_dims == 2:
             x = x.squeeze(2)
         hidden_states_out = [x]
-        x = self.patch_embedding(x)
+        comm = self._sequence_comm()
+        if comm is not None:
+            # rank r owns a contiguous block of rows of the patch grid = a slab of the image along its first spatial
+            # axis (tokens are raster-ordered, reference backbone_vit.py:383): embed only that slab, with its rows of
+            # position_embeddings
+            g0 = self.patch_embedding.grid[0]
+            if g0 % comm.world != 0:
+                raise ValueError(f"sequence parallelism needs the first patch-grid axis ({g0}) divisible by the group "
+                                 f"size ({comm.world})")
+            rows = g0 // comm.world * self.patch_embedding.patch_size[0]
+            x = self.patch_embedding(x.narrow(2, comm.rank * rows, rows), shard=(comm.rank, comm.world))
+        else:
+            x = self.patch_embedding(x)
         if hasattr(self, "cls_token"):
             x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype), x), dim=1)
         # The blocks' arithmetic (reference :260-263) with every residual add folded into the LayerNorm that reads the
@@ -174,4 +231,6 @@ class ViT_with_alt_ops(nn.Module):
         if pending is not None:
             hidden_states_out.append(x)
         hidden_states_out.append(y)
+        if comm is not None and self.gather_outputs:      # the decoders are replicated: hand them whole sequences
+            hidden_states_out = hidden_states_out[:1] + [ring.gather_sequence(h, comm.group) for h in hidden_states_out[1:]]
         return hidden_states_out

@@ -128,15 +128,22 @@ class PatchEmbeddingBlock(nn.Module):
         elif pos_embed_type != "none":
             raise ValueError(f"pos_embed_type {pos_embed_type} not supported")
 
-    def forward(self, x):
+    def forward(self, x, shard=None):
+        """shard = (rank, world): x is this rank's slab of the image along the first spatial axis and the tokens it
+        yields are rows [rank*N/world, (rank+1)*N/world) of the sequence (sequence-parallel encoders)."""
         grid = tuple(s // p for s, p in zip(x.shape[2:], self.patch_size))   # conv floors
         n = 1
         for g in grid:
             n *= g
-        if n != self.n_patches:
+        pos = self.position_embeddings
+        if shard is not None:
+            rank, world = shard
+            if n * world != self.n_patches:
+                raise RuntimeError(f"shard yields {n} patches, expected {self.n_patches} / {world}")
+            pos = pos[:, rank * n:(rank + 1) * n]
+        elif n != self.n_patches:
             raise RuntimeError(f"input yields {n} patches, position embedding has {self.n_patches}")
-        return ops.patch_embed(x, self.patch_embeddings.weight, self.patch_embeddings.bias, self.position_embeddings,
-                               grid, torch.float32)
+        return ops.patch_embed(x, self.patch_embeddings.weight, self.patch_embeddings.bias, pos, grid, torch.float32)
 
 
 class PatchEmbed(nn.Module):

@@ -26,6 +26,11 @@ __global__ void attn_merge_kernel(float* __restrict__ acc, float* __restrict__ l
   const int b = static_cast<int>(bn / N);
   const int64_t lse_idx = (static_cast<int64_t>(b) * H + h) * N + n;                        // lse is (B, H, N)
   const float ls = lse_s[lse_idx];
+  // lane 0 alone reads the running lse and broadcasts it: the same lane overwrites that address below, so no other
+  // lane may still have a load of it in flight (no reliance on the warp staying converged)
+  float la = 0.f;
+  if (!first && lane == 0) la = lse_acc[lse_idx];
+  la = __shfl_sync(0xffffffffu, la, 0);
   const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(o_s + row * 64 + lane * 2);
   float2 x = __bfloat1622float2(v);
   float2 r;
@@ -34,7 +39,6 @@ __global__ void attn_merge_kernel(float* __restrict__ acc, float* __restrict__ l
     r = x;
     lnew = ls;
   } else {
-    const float la = lse_acc[lse_idx];
     const float m = fmaxf(la, ls);
     const float wa = __expf(la - m), ws = __expf(ls - m);
     const float inv = 1.f / (wa + ws);

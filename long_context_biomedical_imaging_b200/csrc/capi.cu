@@ -34,9 +34,15 @@ static void copy3(int64_t* dst, const int64_t* src) {
 
 using namespace lcbi;
 
-static int g_reserved_sms = 0;
+// SMs the persistent dense kernels leave free, per device ordinal (a process may drive several devices)
+static int g_reserved_sms[64] = {0};
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
 namespace lcbi {
-int reserved_sms() { return g_reserved_sms; }
+int reserved_sms() { return __atomic_load_n(&g_reserved_sms[current_device_slot()], __ATOMIC_RELAXED); }
 
 bool first_launch_on_current_device(unsigned long long* seen_mask) {
   int dev = 0;
@@ -72,9 +78,11 @@ int lcbi_version(void) { return LCBI_B200_VERSION; }
 
 int lcbi_set_reserved_sms(int n) {
   if (n < 0 || n > 64) return fail(LCBI_ERR_BAD_ARG, "lcbi_set_reserved_sms: expected 0..64");
-  g_reserved_sms = n;
+  __atomic_store_n(&g_reserved_sms[current_device_slot()], n, __ATOMIC_RELAXED);
   return LCBI_OK;
 }
+
+int lcbi_get_reserved_sms(void) { return lcbi::reserved_sms(); }
 
 const char* lcbi_last_error(void) { return g_err; }
 
@@ -96,8 +104,42 @@ int lcbi_dense_attn_fwd(const void* q, const void* k, const void* v, void* o, fl
   return rc;
 }
 
+int lcbi_dense_attn_fwd_state(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq,
+                              int Nk, int head_dim, const int64_t* q_strides, const int64_t* k_strides,
+                              const int64_t* v_strides, const int64_t* o_strides, float scale, float* state_o,
+                              float* state_m, float* state_l, int first, int last, void* stream) {
+  if (!q || !k || !v || !q_strides || !k_strides || !v_strides || !state_o || !state_m || !state_l)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_fwd_state: null pointer argument");
+  if (last && (!o || !lse || !o_strides))
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_dense_attn_fwd_state: the last step needs o, lse and o_strides");
+  DenseAttnArgs a;
+  a.q = q; a.k = k; a.v = v; a.lse = lse;
+  a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.head_dim = head_dim;
+  copy3(a.q_strides, q_strides); copy3(a.k_strides, k_strides); copy3(a.v_strides, v_strides);
+  if (last) {
+    a.o = o;
+    copy3(a.o_strides, o_strides);
+  } else {                       // nothing is stored through the output map on a non-final step: alias it to q
+    a.o = const_cast<void*>(q);
+    copy3(a.o_strides, q_strides);
+  }
+  a.scale = scale;
+  a.state_o = state_o; a.state_m = state_m; a.state_l = state_l;
+  a.state_first = first ? 1 : 0;
+  a.state_last = last ? 1 : 0;
+  int rc = dense_attn_fwd_launch(a, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_UNSUPPORTED) return fail(rc, "lcbi_dense_attn_fwd_state: only head_dim == 64 is implemented");
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_dense_attn_fwd_state: bad size, or pointer/stride not 16-byte aligned");
+  if (rc == LCBI_ERR_TENSOR_MAP) return fail(rc, "lcbi_dense_attn_fwd_state: TMA tensor map encode failed");
+  return rc;
+}
+
 size_t lcbi_dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim) {
-  return dense_attn_bwd_workspace_bytes(B, H, Nq, head_dim);
+  return dense_attn_bwd_workspace_bytes(B, H, Nq, head_dim, 0);
+}
+
+size_t lcbi_dense_attn_bwd_workspace_bytes_for(int B, int H, int Nq, int head_dim, int accumulate_dq) {
+  return dense_attn_bwd_workspace_bytes(B, H, Nq, head_dim, accumulate_dq);
 }
 
 int lcbi_dense_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,

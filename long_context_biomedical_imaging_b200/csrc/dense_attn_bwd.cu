@@ -67,63 +67,20 @@ __host__ __device__ constexpr int aug_chunk_offset(int row) {   // byte offset o
 // buffer and writes 16 packed columns at [32hh, 32hh+16)); K and V sit in TMEM as the A operands of S^T / dP^T.
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 320, kTmemDQ = 384, kTmemK = 448, kTmemV = 480;
 
-// 1: the drain warps add dQ partials to the fp32 accumulator with red.global from registers; 0: through a swizzled
-// fp32 staging tile and TMA reduce-adds
-#ifndef LCBI_BWD_DQ_RED
-#define LCBI_BWD_DQ_RED 0
-#endif
-
-// 2^x on the FMA / integer pipes: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial of
-// 2^f (relative error 7.5e-5, far below the bf16 rounding P^T gets anyway), n added to the exponent field.
-// 1: warps 0-3 process the even 64-query steps and warps 4-7 the odd ones (all 64 columns each); 0: every compute warp
-// works on every step, warps 0-3 on query columns 0-31 and warps 4-7 on columns 32-63
-#ifndef LCBI_BWD_SPLIT_STEPS
-#define LCBI_BWD_SPLIT_STEPS 0
-#endif
-// 1: the compute warps process their 32 columns in four chunks of 8 inside a rolled loop (see the loop)
-#ifndef LCBI_BWD_CHUNKED
-#define LCBI_BWD_CHUNKED 0
-#endif
-// 1 (experiment; parity-green on a B200 but slower, 0.610 vs 0.48 ms at cfg3: twice the hand-offs and row-term MMAs per
-// query): 32-query pipeline steps with FOUR 32-column S^T / dP^T buffers. Warps 0-3
-// take the even 32-query steps and warps 4-7 the odd ones, each group double-buffered on its own pair of buffers
-// (buffer = 2 * group + (step / 2) % 2), so the two warps of an SM sub-partition run half a step apart without giving
-// up the overlap of a group's compute with the tensor core's work on its other buffer. The Q / dO ring, the dS^T smem
-// tiles, dQ per 128 queries, the epilogue and the drain warps are unchanged; a ring stage (64 queries) serves two steps.
-#ifndef LCBI_BWD_Q32
-#define LCBI_BWD_Q32 0
-#endif
-// > 0: exponentials and the products / packs that consume them are interleaved pair by pair, LAG pairs apart (see the loop)
-#ifndef LCBI_BWD_INTERLEAVE
-#define LCBI_BWD_INTERLEAVE 0
-#endif
-#ifndef LCBI_BWD_POLY_EXP
-#define LCBI_BWD_POLY_EXP 0
-#endif
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;             // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float r = fmaf(f, 0.0551716648f, 0.2426111251f);
-  r = fmaf(f, r, 0.6932609677f);
-  r = fmaf(f, r, 0.9999280572f);
-  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
-}
-
 struct __align__(1024) BwdSmem {
   uint8_t k[2][kTileBytes];             // K of item it in k[it & 1]: the next item's K is prefetched during this one
   uint8_t v[kTileBytes];                // only read by the copy into TMEM, so the next item's V can follow early too
   uint8_t q[kQStages][kStepBytes];      // 64-query tiles; together also the dK staging area of the epilogue
   uint8_t dout[kQStages][kStepBytes];   // likewise dV staging
   uint8_t ds[2][2 * kTileBytes];        // dS^T per 128-query tile (double-buffered): two [128 keys x 64 queries] atoms
-  uint8_t dq_stage[LCBI_BWD_DQ_RED ? 1024 : 2 * kTileBytes];   // two [128 queries x 32 fp32] SW128 tiles (TMA-reduce drain)
+  uint8_t dq_stage[2 * kTileBytes];               // two [128 queries x 32 fp32] SW128 tiles (TMA-reduce drain)
   uint8_t lse_aug[kQStages][kAugBytes];   // per-query -lse/scale as the B operand of one extra k-step of S^T
   uint8_t d_aug[kQStages][kAugBytes];     // per-query -D likewise for dP^T
   uint8_t ones[2 * kAugBytes];            // [128 keys x 8] constant A operand of those k-steps: (1, 1, 1, 0, ...)
   uint8_t aug_zeros[2 * kAugBytes];       // second k-half of every row-term tile (placed after them: LBO > 0)
   uint64_t k_full[2], v_full;
   uint64_t q_full[kQStages], q_empty[kQStages], do_full[kQStages], do_empty[kQStages];
-  uint64_t sdp_full[LCBI_BWD_Q32 ? 4 : 2], pds_full[LCBI_BWD_Q32 ? 4 : 2], kvt_full, dq_full, dq_empty, dkv_full, dkv_drained;
+  uint64_t sdp_full[2], pds_full[2], kvt_full, dq_full, dq_empty, dkv_full, dkv_drained;
   uint32_t tmem_base;
 };
 
@@ -162,7 +119,6 @@ struct BwdParams {
   const __nv_bfloat16* d_aug;     // likewise -D, D = rowsum(dO o O)
   float* dq_acc;       // fp32 (B,Nq,H,64) accumulator
   int accumulate_dkv;
-  uint32_t zero_bits;  // always 0; opaque to the compiler (LCBI_BWD_INTERLEAVE)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -319,9 +275,9 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_init(&sm.do_full[s], 1);
       mbar_init(&sm.do_empty[s], 1);
     }
-    for (int b = 0; b < (LCBI_BWD_Q32 ? 4 : 2); ++b) {
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.sdp_full[b], 1);
-      mbar_init(&sm.pds_full[b], (LCBI_BWD_SPLIT_STEPS || LCBI_BWD_Q32) ? 4 : 8);   // one arrive per compute warp working on the buffer
+      mbar_init(&sm.pds_full[b], 8);       // one arrive per compute warp
     }
     mbar_init(&sm.kvt_full, 8);
     mbar_init(&sm.dq_full, 1);
@@ -436,71 +392,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         umma_commit(&sm.sdp_full[b]);
       };
 
-#if LCBI_BWD_Q32
-      // 32-query steps: global step counter g32 = it * n32 + s; ring stage of a step = its 64-query index (g32 >> 1);
-      // S^T / dP^T buffer j = 2 * (g32 & 1) + ((g32 >> 1) & 1) at columns 32 j, used every fourth step (phase g32 >> 2)
-      constexpr uint32_t idesc_nt32 = make_idesc_bf16(kTile, 32, 0, 0);
-      const int n32 = 2 * n_steps;
-      auto buf_of = [](int g32) { return 2 * (g32 & 1) + ((g32 >> 1) & 1); };
-      auto issue_sdp32 = [&](int g32) {
-        const int gst = g32 >> 1, st = gst % kQStages, h = g32 & 1, j = buf_of(g32);
-        // rows 32 h .. 32 h + 31 of the stage's tiles: 4 KB into the swizzled Q / dO tile, 512 B into the row-term tiles
-        const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes + h * 4096), ddo_s = desc_advance(d_do0, st * kStepBytes + h * 4096);
-#pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)
-          umma_ts(tmem + kTmemS + j * 32, tmem + kTmemK + kk * 8, desc_advance(dq_s, kk * 32), idesc_nt32, kk > 0 ? 1u : 0u);
-        umma_ss(tmem + kTmemS + j * 32, d_ones, aug_stage(d_lse0, st) + (h * 512 >> 4), idesc_nt32, 1u);
-#pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)
-          umma_ts(tmem + kTmemDP + j * 32, tmem + kTmemV + kk * 8, desc_advance(ddo_s, kk * 32), idesc_nt32, kk > 0 ? 1u : 0u);
-        umma_ss(tmem + kTmemDP + j * 32, d_ones, aug_stage(d_d0, st) + (h * 512 >> 4), idesc_nt32, 1u);
-        umma_commit(&sm.sdp_full[j]);
-      };
-      int it = 0;
-      for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
-        const int g0 = it * n32, gi0 = it * n_tiles;
-        const uint64_t d_k = desc_advance(d_k0, (it & 1) * kTileBytes);
-        mbar_wait(&sm.kvt_full, it & 1);
-        for (int s = 0; s < 4; ++s) {          // n32 >= 4: Nq_pad is a multiple of 128
-          if ((s & 1) == 0) wait_sdp_operands((g0 + s) >> 1);
-          tc_fence_after();
-          issue_sdp32(g0 + s);
-        }
-        for (int s = 0; s < n32; ++s) {
-          const int g32 = g0 + s, gst = g32 >> 1, st = gst % kQStages, h = g32 & 1, j = buf_of(g32), gi = gi0 + (s >> 2);
-          if (s + 4 < n32 && (s & 1) == 0) wait_sdp_operands((g32 + 4) >> 1);
-          if ((s & 3) == 3) mbar_wait(&sm.dq_empty, (gi & 1) ^ 1);
-          if (s == 0 && it > 0) mbar_wait(&sm.dkv_drained, (it - 1) & 1);
-          mbar_wait(&sm.pds_full[j], (g32 >> 2) & 1);
-          tc_fence_after();
-          const uint64_t dq_s = desc_advance(d_q0, st * kStepBytes), ddo_s = desc_advance(d_do0, st * kStepBytes);
-          // dV += P^T dO, dK += dS^T Q over this step's 32 queries: two k-steps of 16 (8 packed columns each); the B
-          // operand rows are queries 32 h + 16 kk of the 64-query stage tile
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
-            umma_ts(tmem + kTmemDV, tmem + kTmemS + j * 32 + kk * 8, desc_advance(ddo_s, (2 * h + kk) * 2048), idesc_kmn,
-                    (s > 0 || kk > 0) ? 1u : 0u);
-          if (h) umma_commit(&sm.do_empty[st]);
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
-            umma_ts(tmem + kTmemDK, tmem + kTmemDP + j * 32 + kk * 8, desc_advance(dq_s, (2 * h + kk) * 2048), idesc_kmn,
-                    (s > 0 || kk > 0) ? 1u : 0u);
-          if (h) umma_commit(&sm.q_empty[st]);
-          if (s + 4 < n32) issue_sdp32(g32 + 4);
-          if ((s & 3) == 3) {
-            const uint64_t dds_mn = desc_advance(d_ds_mn0, (gi & 1) * 2 * kTileBytes);
-#pragma unroll
-            for (int kk = 0; kk < kTile / 16; ++kk)
-              umma_ss(tmem + kTmemDQ, desc_advance(dds_mn, kk * 2048), desc_advance(d_k, kk * 2048), idesc_mnmn,
-                      kk > 0 ? 1u : 0u);
-            umma_commit(&sm.dq_full);
-          }
-        }
-        umma_commit(&sm.dkv_full);
-      }
-      (void)idesc_nt;
-      (void)issue_sdp;
-#else
       int it = 0;
       for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
         const int gs0 = it * n_steps, gi0 = it * n_tiles;
@@ -555,7 +446,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         umma_commit(&sm.dkv_full);
       }
-#endif
     }
   } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ dQ drain (warps 8-11)
@@ -571,60 +461,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mbar_wait(&sm.dq_full, gi & 1);
         if (issuer && it == 0) LCBI_TR(3, i, 0);
         tc_fence_after();
-#if LCBI_BWD_DQ_RED
-        // dQ partials go from registers straight into the fp32 accumulator: with the 16x256b fragment layout a quad
-        // of threads owns 32 contiguous bytes of one query row, so every red.v2 quad fills one whole L2 sector
-        // (no staging tile, no TMA reduce, no barriers among the drain warps).
-        {
-          uint32_t ra[32], rb[32];
-          tmem_ld_16x256b_x8(t_dq, ra);                  // query rows  0-15 of this warp's 32
-          tmem_ld_16x256b_x8(t_dq + (16u << 16), rb);    // query rows 16-31
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.dq_empty);
-          const int q0 = i * kTile + (warp & 3) * 32 + (lane >> 2);
-          float* const col0 = p.dq_acc + (static_cast<size_t>(batch) * p.Nq * p.H + head) * kHeadDim + (lane & 3) * 2;
-#if LCBI_BWD_DQ_RED == 2
-          // neighbours in a quad swap pairs, so that the even thread owns four contiguous columns of row g and the odd
-          // thread the same four columns of row g + 8: half as many (16-byte) reds, two of them fill a sector
-          const bool odd = lane & 1;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t* r = half ? rb : ra;
-            const int q = q0 + half * 16 + (odd ? 8 : 0);
-            float* dst = col0 - (odd ? 2 : 0) + static_cast<size_t>(q) * p.H * kHeadDim;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              // even keeps (r0, r1) of row g and receives the odd neighbour's (r0, r1); odd keeps (r2, r3) of row g + 8
-              // and receives the even neighbour's (r2, r3)
-              const uint32_t s0 = odd ? r[4 * j] : r[4 * j + 2], s1 = odd ? r[4 * j + 1] : r[4 * j + 3];
-              const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-              const float a0 = __uint_as_float(odd ? x0 : r[4 * j]), a1 = __uint_as_float(odd ? x1 : r[4 * j + 1]);
-              const float a2 = __uint_as_float(odd ? r[4 * j + 2] : x0), a3 = __uint_as_float(odd ? r[4 * j + 3] : x1);
-              if (q < p.Nq) red_add_f32x4(dst + j * 8, a0 * p.scale, a1 * p.scale, a2 * p.scale, a3 * p.scale);
-            }
-          }
-#else
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t* r = half ? rb : ra;
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              const int q = q0 + half * 16 + v * 8;
-              if (q < p.Nq) {
-                float* dst = col0 + static_cast<size_t>(q) * p.H * kHeadDim;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  red_add_f32x2(dst + j * 8, __uint_as_float(r[4 * j + 2 * v]) * p.scale,
-                                __uint_as_float(r[4 * j + 2 * v + 1]) * p.scale);
-              }
-            }
-          }
-#endif
-          if (issuer && it == 0) LCBI_TR(3, i, 1);
-        }
-#else
         uint32_t r[64];
         tmem_ld_x32(t_dq, r);
         tmem_ld_x32(t_dq + 32, r + 32);
@@ -650,7 +486,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tma_store_commit();
         }
         if (issuer && it == 0) LCBI_TR(3, i, 1);
-#endif
       }
     }
     if (issuer) tma_store_wait_read<0>();
@@ -665,10 +500,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     bool store_pending = false;                 // the previous item's dV/dK store may still be reading its staging tiles
     auto finish_store = [&]() {
       if (store_issuer) tma_store_wait_read<0>();
-#if LCBI_BWD_SPLIT_STEPS && !LCBI_BWD_Q32
-      if (!p.accumulate_dkv) named_bar_sync(5 + hh, 128);   // the staging atom is this group's own
-      else
-#endif
       named_bar_sync(7, 256);
       store_pending = false;
     };
@@ -701,94 +532,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       LCBI_ITEM_T(0);
       if (it == 0) copy_kv_to_tmem(0);           // later items: done at the end of the previous item's last step
 
-#if LCBI_BWD_Q32
-      // 32-query steps (see LCBI_BWD_Q32 at the top): this group's steps are s = hh, hh + 2, ...; all 32 columns of the
-      // step's buffer belong to this thread's key row
-      const int n32 = 2 * n_steps, g0 = it * n32;
-      for (int s = hh; s < n32; s += 2) {
-        const int g32 = g0 + s, j = 2 * hh + ((g32 >> 1) & 1), gi = gi0 + (s >> 2);
-        // the previous item's dV / dK staging tiles are the two atoms of this item's second 128-query tile, each of
-        // which both groups write (steps 4, 5 / 6, 7): both stores must have been read before either group gets there
-        if (store_pending && (p.accumulate_dkv || s == 4 + hh)) finish_store();
-        mbar_wait(&sm.sdp_full[j], (g32 >> 2) & 1);
-        tc_fence_after();
-        uint32_t sv[32], dpv[32];
-        tmem_ld_x32(tmem + lane_sel + kTmemS + j * 32, sv);
-        tmem_ld_x32(tmem + lane_sel + kTmemDP + j * 32, dpv);
-        tmem_ld_wait();
-        uint32_t pk[16], dsk[16];
-        // dS^T smem atom = the 64-query half of the 128-query tile this step lies in; 16-byte chunks 4 h .. 4 h + 3
-        uint8_t* ds_atom = sm.ds[gi & 1] + ((s >> 1) & 1) * kTileBytes;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
-          pk[e >> 1] = pack_bf16x2(p0, p1);
-          dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
-                       "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
-        tmem_st_x16(tmem + lane_sel + kTmemS + j * 32, pk);
-        tmem_st_x16(tmem + lane_sel + kTmemDP + j * 32, dsk);
-        tmem_st_wait();
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.pds_full[j]);
-      }
-      // all S^T / dP^T GEMMs of the item must have retired before K / V of the next item replace this item's in TMEM:
-      // this thread consumed its own group's; the other group's last two steps are waited for here (those barriers
-      // cannot complete another phase before this thread has copied its rows)
-      for (int back = 0; back < 2; ++back) {
-        const int s_o = n32 - 1 - hh - 2 * back, g_o = g0 + s_o;      // steps of the other parity: n32 - 1 - hh, minus 2
-        mbar_wait(&sm.sdp_full[2 * (1 - hh) + ((g_o >> 1) & 1)], (g_o >> 2) & 1);
-      }
-#elif LCBI_BWD_SPLIT_STEPS
-      // Warps 0-3 take the even steps, warps 4-7 the odd ones, each all 64 query columns of its step (two passes of 32).
-      // A group then always works on the same S^T / dP^T buffer (b == hh), and the two warps that share an SM
-      // sub-partition run half a step apart: one is in its MUFU burst while the other packs, stores and fences.
-      for (int s = hh; s < n_steps; s += 2) {
-        const int gs = gs0 + s, b = gs & 1, gi = gi0 + (s >> 1);
-        // staging tile of this group's previous dV / dK store = the dS^T atom this group writes at step 2 + hh
-        // (fp32 accumulate mode: both buffers, so both groups meet at their first step)
-        if (store_pending && (p.accumulate_dkv || s == 2 + hh)) finish_store();
-        mbar_wait(&sm.sdp_full[b], (gs >> 1) & 1);
-        tc_fence_after();
-        uint8_t* ds_atom = sm.ds[gi & 1] + (s & 1) * kTileBytes;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t sv[32], dpv[32];
-          tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + half * 32, sv);
-          tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + half * 32, dpv);
-          tmem_ld_wait();
-          uint32_t pk[16], dsk[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
-            pk[e >> 1] = pack_bf16x2(p0, p1);
-            dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, half * 4 + g))),
-                         "r"(dsk[g * 4]), "r"(dsk[g * 4 + 1]), "r"(dsk[g * 4 + 2]), "r"(dsk[g * 4 + 3]) : "memory");
-          tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + half * 32, pk);
-          tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + half * 32, dsk);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.pds_full[b]);
-      }
-      // the other group's last S^T / dP^T GEMMs must have retired too before K / V of the next item replace this
-      // item's in TMEM (that barrier cannot complete another phase before this thread has copied its rows)
-      {
-        const int s_other = n_steps - 1 - hh;     // last step of the other parity
-        mbar_wait(&sm.sdp_full[s_other & 1], ((gs0 + s_other) >> 1) & 1);
-      }
-#else
       for (int s = 0; s < n_steps; ++s) {
         const int gs = gs0 + s, b = gs & 1, gi = gi0 + (s >> 1);
         // the staging tiles of the previous item's dV/dK store live in the dS^T buffer of this item's SECOND tile
@@ -802,48 +545,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 1);
         tc_fence_after();
         uint8_t* ds_atom = sm.ds[gi & 1] + (s & 1) * kTileBytes;
-#if LCBI_BWD_CHUNKED
-        // The 32 columns go through in four chunks of 8 inside a real (not unrolled) loop, so that the compiler cannot
-        // hoist all 32 MUFU.EX2 into one burst that blocks the warp for 256+ cycles: a chunk's packing / stores then
-        // issue while the sibling warp of the SM sub-partition owns the MUFU pipe. Chunks alternate between two
-        // register sets; the next chunk's TMEM load is in flight while the current one is processed.
-        {
-          const uint32_t t_s = tmem + lane_sel + kTmemS + b * kStep + hh * 32;
-          const uint32_t t_dp = tmem + lane_sel + kTmemDP + b * kStep + hh * 32;
-          auto chunk = [&](const uint32_t* sx, const uint32_t* dx, int col) {   // columns [col, col + 8) of this thread's 32
-            uint32_t pk4[4], ds4[4];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const float p0 = fast_exp2(__uint_as_float(sx[e]) * c), p1 = fast_exp2(__uint_as_float(sx[e + 1]) * c);
-              pk4[e >> 1] = pack_bf16x2(p0, p1);
-              ds4[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dx[e]), p1 * __uint_as_float(dx[e + 1]));
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + (col >> 3)))),
-                         "r"(ds4[0]), "r"(ds4[1]), "r"(ds4[2]), "r"(ds4[3]) : "memory");
-            // in place: 8 columns read -> 4 packed columns written at half the offset (always columns already consumed)
-            tmem_st_x4(t_s + (col >> 1), pk4);
-            tmem_st_x4(t_dp + (col >> 1), ds4);
-          };
-          uint32_t sa[8], da[8], sb[8], db[8];
-          tmem_ld_x8(t_s, sa);
-          tmem_ld_x8(t_dp, da);
-          tmem_ld_wait();
-#pragma unroll 1
-          for (int k2 = 0; k2 < 2; ++k2) {
-            const int c0 = k2 * 16;
-            tmem_ld_x8(t_s + c0 + 8, sb);
-            tmem_ld_x8(t_dp + c0 + 8, db);
-            chunk(sa, da, c0);
-            tmem_ld_wait();
-            if (k2 == 0) {
-              tmem_ld_x8(t_s + 16, sa);
-              tmem_ld_x8(t_dp + 16, da);
-            }
-            chunk(sb, db, c0 + 8);
-            tmem_ld_wait();
-          }
-        }
-#else
         uint32_t sv[32], dpv[32];
         tmem_ld_x32(tmem + lane_sel + kTmemS + b * kStep + hh * 32, sv);
         tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dpv);
@@ -851,34 +552,12 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 2);
         uint32_t pk[16], dsk[16];
         // the per-query terms were already added by the tensor core: sv = q.k - lse/scale, dpv = dO.v - D
-#if LCBI_BWD_INTERLEAVE
-        // Left alone, the compiler hoists all 32 MUFU.EX2 into one burst; the warp then sits on the 16 / clk / SM MUFU
-        // pipe for the whole burst and only afterwards multiplies, packs and stores, and its sibling warp on the SM
-        // sub-partition does the same in lockstep. A data dependency forces the interleave instead: the exponent of
-        // pair i gets (bits & 0) of the packed result of pair i - LAG added, with the 0 a kernel parameter the compiler
-        // cannot fold. The products / packs of one pair then issue under the MUFU time of the next ones.
-        uint32_t tok[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const int i = e >> 1;
-          const float z = i >= LCBI_BWD_INTERLEAVE ? __uint_as_float(tok[i >= LCBI_BWD_INTERLEAVE ? i - LCBI_BWD_INTERLEAVE : 0]) : 0.0f;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c, z)), p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c, z));
-          pk[i] = pack_bf16x2(p0, p1);
-          dsk[i] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
-          tok[i] = (pk[i] | dsk[i]) & p.zero_bits;
-        }
-#else
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c);
-          // LCBI_BWD_POLY_EXP of every 32 exponentials run on the FMA pipe instead of the (16 / clk / SM) MUFU pipe
-          const bool poly = (LCBI_BWD_POLY_EXP == 16) || (LCBI_BWD_POLY_EXP == 8 && (e & 2)) ||
-                            (LCBI_BWD_POLY_EXP == 4 && (e & 6) == 6);
-          const float p1 = poly ? poly_exp2(__uint_as_float(sv[e + 1]) * c) : fast_exp2(__uint_as_float(sv[e + 1]) * c);
+          const float p0 = fast_exp2(__uint_as_float(sv[e]) * c), p1 = fast_exp2(__uint_as_float(sv[e + 1]) * c);
           pk[e >> 1] = pack_bf16x2(p0, p1);
           dsk[e >> 1] = pack_bf16x2(p0 * __uint_as_float(dpv[e]), p1 * __uint_as_float(dpv[e + 1]));
         }
-#endif
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ds_atom + sw128_offset(row, hh * 4 + g))),
@@ -886,7 +565,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // in place: the packed results overwrite the first 16 of the 32 columns this thread just read
         tmem_st_x16(tmem + lane_sel + kTmemS + b * kStep + hh * 32, pk);
         tmem_st_x16(tmem + lane_sel + kTmemDP + b * kStep + hh * 32, dsk);
-#endif
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 3);
         tmem_st_wait();
         tc_fence_before();
@@ -896,7 +574,6 @@ dense_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (lane == 0 && it == 0) LCBI_TR(hh, s, 4);
       }
 
-#endif
       // The S^T / dP^T GEMMs of this item have all retired (this thread consumed the last of them), so K and V of the
       // next item can take their place in TMEM now: its first GEMMs then run while this item's epilogue drains dV / dK.
       LCBI_ITEM_T(3);
@@ -997,9 +674,10 @@ extern "C" int lcbi_debug_set_bwd_item_times(long long* ptr) {
 }
 #endif
 
-size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim) {
+// Workspace = [fp32 dQ accumulator (B,Nq,H,64), absent when the caller accumulates into its own] [-lse/scale tiles] [-D tiles]
+size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim, int accumulate_dq) {
   const size_t nq_pad = align_up(static_cast<size_t>(Nq), kTile);
-  const size_t acc = align_up(static_cast<size_t>(B) * Nq * H * head_dim * 4, 128);
+  const size_t acc = accumulate_dq ? 0 : align_up(static_cast<size_t>(B) * Nq * H * head_dim * 4, 128);
   const size_t vec = align_up(static_cast<size_t>(B) * H * (nq_pad / kStep) * kAugBytes, 128);
   return acc + 2 * vec;
 }
@@ -1015,12 +693,12 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   const void* ptrs[] = {a.q, a.k, a.v, a.o, a.d_o, a.dq, a.dk, a.dv};
   for (const void* ptr : ptrs)
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return LCBI_ERR_BAD_ARG;
-  if (a.workspace_bytes < dense_attn_bwd_workspace_bytes(a.B, a.H, a.Nq, a.head_dim) ||
+  if (a.workspace_bytes < dense_attn_bwd_workspace_bytes(a.B, a.H, a.Nq, a.head_dim, a.accumulate_dq) ||
       (reinterpret_cast<uintptr_t>(a.workspace) & 127))
     return LCBI_ERR_WORKSPACE;
 
   const int nq_pad = static_cast<int>(align_up(static_cast<size_t>(a.Nq), kTile));
-  const size_t acc_bytes = align_up(static_cast<size_t>(a.B) * a.Nq * a.H * kHeadDim * 4, 128);
+  const size_t acc_bytes = a.accumulate_dq ? 0 : align_up(static_cast<size_t>(a.B) * a.Nq * a.H * kHeadDim * 4, 128);
   const size_t vec_bytes = align_up(static_cast<size_t>(a.B) * a.H * (nq_pad / kStep) * kAugBytes, 128);
   float* dq_acc = a.accumulate_dq ? reinterpret_cast<float*>(a.dq) : reinterpret_cast<float*>(a.workspace);
   uint8_t* lse_aug = reinterpret_cast<uint8_t*>(a.workspace) + acc_bytes;
@@ -1070,7 +748,6 @@ int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream) {
   p.d_aug = reinterpret_cast<const __nv_bfloat16*>(d_aug);
   p.dq_acc = dq_acc;
   p.accumulate_dkv = a.accumulate_dkv;
-  p.zero_bits = 0u;
   const int num_sms = current_device_sm_count();
   if (num_sms <= 0) return LCBI_ERR_CUDA;
   p.n_kv_tiles = (a.Nk + kTile - 1) / kTile;

@@ -72,6 +72,13 @@ struct FwdParams {
   int n_q_tiles, n_items;
   float scale_log2;   // scale * log2(e)
   float* lse;         // (B, H, Nq) natural log
+  // Ring steps (lcbi_dense_attn_fwd_state): the online-softmax state of every query row is carried across launches,
+  // one launch per visiting K/V shard, so the shards fold into ONE running result without a merge pass.
+  float* st_o;        // fp32 (B, Nq, H, 64) un-normalised running output, or nullptr (plain call)
+  float* st_m;        // fp32 (B, H, Nq) running max actually subtracted, raw score units
+  float* st_l;        // fp32 (B, H, Nq) running row sum
+  int carry_in;       // 1: start every row from (st_o, st_m, st_l) instead of (0, -inf, 0)
+  int carry_out;      // 1: write the state back instead of the normalised bf16 output and lse
 };
 
 // Timing-only ablations (results become wrong; every barrier still fires): bit 0 no exp2, bit 1 no row-max pass,
@@ -81,6 +88,8 @@ struct FwdParams {
 #endif
 constexpr int kAblate = LCBI_FWD_ABLATE;
 
+// kCarry: the ring-step variant (state carried in / out); the plain kernel compiles without any of that code
+template <bool kCarry>
 __global__ void __launch_bounds__(kNumThreads, kCtasPerSm)
 dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -179,7 +188,7 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           umma_commit(&sm.s_full[g & 1]);
         };
-        auto issue_pv = [&](int g, bool first) {  // O (+)= P(g) V(g)
+        auto issue_pv = [&](int g, bool first) {  // O (+)= P(g) V(g); with a carried-in state O is never overwritten
           const uint32_t v_addr = smem_u32(sm.v[g % kStages]);
 #pragma unroll
           for (int kk = 0; kk < kBlockN / 16; ++kk) {
@@ -206,7 +215,7 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           mbar_wait(&sm.p_full[g & 1], (g >> 1) & 1);
           LCBI_TR(1, j, 0);
           tc_fence_after();
-          issue_pv(g, j == 0);
+          issue_pv(g, j == 0 && !(kCarry && p.carry_in));
           if (has_next) issue_s(g + 2);
           else if (j == n_kv - 1) umma_commit(&sm.o_full);
           umma_commit(&sm.v_empty[g % kStages]);
@@ -229,6 +238,31 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       decode(item, batch, head, q_base);
       float m_used = -INFINITY;  // running max actually subtracted (raw score units)
       float l = 0.f;
+      const int q_row_st = q_base + row;
+      const bool row_valid = q_row_st < p.Nq;
+      if (kCarry && p.carry_in) {
+        // the state of the previous ring steps: O goes back into TMEM before the first P V of this item is issued (the
+        // issuer waits for p_full of the first K/V tile, which this thread signals only after these stores)
+        const size_t ml_idx = (static_cast<size_t>(batch) * p.H + head) * p.Nq + q_row_st;
+        if (row_valid) {
+          m_used = p.st_m[ml_idx];
+          l = p.st_l[ml_idx];
+        }
+        const float4* src = reinterpret_cast<const float4*>(
+            p.st_o + ((static_cast<size_t>(batch) * p.Nq + (row_valid ? q_row_st : 0)) * p.H + head) * kHeadDim);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = row_valid ? src[half * 8 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[4 * i] = __float_as_uint(x.x); o[4 * i + 1] = __float_as_uint(x.y);
+            o[4 * i + 2] = __float_as_uint(x.z); o[4 * i + 3] = __float_as_uint(x.w);
+          }
+          tmem_st_x32(t_o + half * 32, o);
+        }
+        tmem_st_wait();
+      }
 
       for (int j = 0; j < n_kv; ++j) {
         const int g = g0 + j;
@@ -274,10 +308,11 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const float alpha = need ? fast_exp2((m_used - m_new) * c) : 1.0f;
           if (need) m_used = m_new;
           l *= alpha;
-          if (j > 0) {
+          if (j > 0 || (kCarry && p.carry_in)) {
             // O must be quiescent: P(g-1) V has completed (the S buffers are double-buffered, so s_full alone
-            // does not imply it) and P(g) V is not issued before this warp group signals p_full.
-            mbar_wait(&sm.pv_done, (g - 1) & 1);
+            // does not imply it) and P(g) V is not issued before this warp group signals p_full. (j == 0 with a
+            // carried-in state: O was just written by this very thread and no P V of the item exists yet.)
+            if (j > 0) mbar_wait(&sm.pv_done, (g - 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -337,6 +372,23 @@ dense_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tma_store_wait_read<0>();
         mbar_arrive(&sm.q_free[store_pending]);
         store_pending = -1;
+      }
+      if (kCarry && p.carry_out) {
+        // ring step that is not the last: the un-normalised state goes back to HBM, nothing is staged or TMA-stored,
+        // and the item's Q tile (dead since o_full) returns to the producer right away
+        if (tid == 0) mbar_arrive(&sm.q_free[it & 1]);
+        if (row_valid) {
+          const size_t ml_idx = (static_cast<size_t>(batch) * p.H + head) * p.Nq + q_row_st;
+          p.st_m[ml_idx] = m_used;
+          p.st_l[ml_idx] = l;
+          float4* dst = reinterpret_cast<float4*>(
+              p.st_o + ((static_cast<size_t>(batch) * p.Nq + q_row_st) * p.H + head) * kHeadDim);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            dst[i] = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                                 __uint_as_float(o[4 * i + 3]));
+        }
+        continue;
       }
       const float inv_l = 1.0f / l;
       uint8_t* stage = sm.q[it & 1];
@@ -403,7 +455,9 @@ int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream) {
   static unsigned long long configured = 0;   // one bit per device ordinal
   const int smem_bytes = static_cast<int>(sizeof(FwdSmem)) + 1024;
   if (first_launch_on_current_device(&configured)) {
-    cudaError_t e = cudaFuncSetAttribute(dense_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(dense_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       configured = 0;
       return set_cuda_error(e);
@@ -417,9 +471,17 @@ int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream) {
   p.n_items = p.n_q_tiles * a.H * a.B;
   p.scale_log2 = a.scale * kLog2e;
   p.lse = a.lse;
+  p.st_o = a.state_o; p.st_m = a.state_m; p.st_l = a.state_l;
+  p.carry_in = (a.state_o != nullptr && !a.state_first) ? 1 : 0;
+  p.carry_out = (a.state_o != nullptr && !a.state_last) ? 1 : 0;
+  if (a.state_o != nullptr && (a.state_m == nullptr || a.state_l == nullptr)) return LCBI_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(a.state_o) & 15) return LCBI_ERR_BAD_ARG;
   const int slots = kCtasPerSm * (num_sms - reserved_sms() > 1 ? num_sms - reserved_sms() : 1);
   dim3 grid(p.n_items < slots ? p.n_items : slots);
-  dense_attn_fwd_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, to, p);
+  if (a.state_o != nullptr && !(a.state_first && a.state_last))
+    dense_attn_fwd_kernel<true><<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, to, p);
+  else
+    dense_attn_fwd_kernel<false><<<grid, kNumThreads, smem_bytes, stream>>>(tq, tk, tv, to, p);
   return set_cuda_error(cudaGetLastError());
 }
 

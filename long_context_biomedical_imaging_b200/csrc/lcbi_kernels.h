@@ -19,6 +19,12 @@ struct DenseAttnArgs {
   int B, H, Nq, Nk, head_dim;
   int64_t q_strides[3], k_strides[3], v_strides[3], o_strides[3];  // (batch, row, head) in elements
   float scale;
+  // carried online-softmax state (ring steps); all nullptr / 0 for a plain call
+  float* state_o = nullptr;   // fp32 (B, Nq, H, d) contiguous, un-normalised running output
+  float* state_m = nullptr;   // fp32 (B, H, Nq) running max (raw score units)
+  float* state_l = nullptr;   // fp32 (B, H, Nq) running sum
+  int state_first = 0;        // 1: the incoming state is ignored (first K/V shard)
+  int state_last = 0;         // 1: normalise and write o (bf16) + lse; otherwise only the state is written back
 };
 int dense_attn_fwd_launch(const DenseAttnArgs& a, cudaStream_t stream);
 
@@ -34,7 +40,7 @@ struct DenseAttnBwdArgs {
   int accumulate_dkv;   // 0: write bf16 dk/dv; 1: dk/dv are fp32 (B,Nk,H,d) contiguous accumulators (+=)
   int accumulate_dq;    // 0: write bf16 dq;    1: dq is an fp32 (B,Nq,H,d) contiguous accumulator (+=)
 };
-size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim);
+size_t dense_attn_bwd_workspace_bytes(int B, int H, int Nq, int head_dim, int accumulate_dq);
 int dense_attn_bwd_launch(const DenseAttnBwdArgs& a, cudaStream_t stream);
 
 // SMs the persistent dense kernels leave free (for communication kernels running beside them); capi.cu

@@ -13,13 +13,29 @@ from . import _lib
 
 
 def _require_cuda(*tensors):
+    """All operands must live on ONE CUDA device. Returns that device (None when every operand is None)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("lcbi_b200 operators need CUDA tensors: there is no CPU fallback for the attention hot path")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"lcbi_b200 operators need all operands on one device, got {dev} and {t.device}")
+    return dev
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _on(dev):
+    """Device guard for a launch: the library reads the SM count, its per-device launch caches and the TMA encode from
+    the CURRENT device, so the operands' device is made current for the duration of the call."""
+    return torch.cuda.device(dev)
+
+
+def _stream(dev):
+    """The caller's current stream ON THE OPERANDS' DEVICE (not the process-wide current device's)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _p(t):
@@ -38,62 +54,126 @@ def _bnhd_strides(t):
 # --------------------------------------------------------------------------------------------------
 def dense_attn_fwd(q, k, v, scale, out=None):
     """q: (B,Nq,H,64), k/v: (B,Nk,H,64) bf16 views. Returns (o (B,Nq,H,64) bf16, lse (B,H,Nq) fp32)."""
-    _require_cuda(q, k, v)
+    dev = _require_cuda(q, k, v, out)
     if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
         raise ValueError("dense_attn_fwd expects bf16 tensors")
     B, Nq, H, d = q.shape
     Nk = k.shape[1]
     if k.shape != (B, Nk, H, d) or v.shape != (B, Nk, H, d):
         raise ValueError("q/k/v shape mismatch")
-    o = out if out is not None else torch.empty((B, Nq, H, d), dtype=torch.bfloat16, device=q.device)
-    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    if out is not None and (out.dtype != torch.bfloat16 or out.shape != (B, Nq, H, d)):
+        raise ValueError("dense_attn_fwd: `out` must be a bf16 (B, Nq, H, d) view")
+    o = out if out is not None else torch.empty((B, Nq, H, d), dtype=torch.bfloat16, device=dev)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=dev)
     lib = _lib.load()
-    rc = lib.lcbi_dense_attn_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Nq, Nk, d, _bnhd_strides(q),
-                                 _bnhd_strides(k), _bnhd_strides(v), _bnhd_strides(o), float(scale), _stream())
+    with _on(dev):
+        rc = lib.lcbi_dense_attn_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Nq, Nk, d, _bnhd_strides(q),
+                                     _bnhd_strides(k), _bnhd_strides(v), _bnhd_strides(o), float(scale), _stream(dev))
     _lib.check(rc, "lcbi_dense_attn_fwd")
     return o, lse
+
+
+def dense_attn_fwd_state(q, k, v, scale, state, first, last, out=None, lse=None):
+    """One ring step of the forward (C ABI lcbi_dense_attn_fwd_state): folds the K/V shard (k, v) into the carried
+    online-softmax state of the local query rows. state = (o_acc fp32 (B,Nq,H,64), m fp32 (B,H,Nq), l fp32 (B,H,Nq)),
+    all contiguous; `first` ignores the incoming state; `last` normalises and writes `out` (bf16) and `lse` (both are
+    allocated when not given) and returns them, otherwise only the state is updated and (None, None) is returned."""
+    st_o, st_m, st_l = state
+    dev = _require_cuda(q, k, v, st_o, st_m, st_l, out, lse)
+    if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+        raise ValueError("dense_attn_fwd_state expects bf16 q/k/v")
+    B, Nq, H, d = q.shape
+    Nk = k.shape[1]
+    if k.shape != (B, Nk, H, d) or v.shape != (B, Nk, H, d):
+        raise ValueError("q/k/v shape mismatch")
+    if (st_o.dtype != torch.float32 or tuple(st_o.shape) != (B, Nq, H, d) or not st_o.is_contiguous()):
+        raise ValueError("dense_attn_fwd_state: state[0] must be a contiguous fp32 (B, Nq, H, d) tensor")
+    for t in (st_m, st_l):
+        if t.dtype != torch.float32 or tuple(t.shape) != (B, H, Nq) or not t.is_contiguous():
+            raise ValueError("dense_attn_fwd_state: state[1], state[2] must be contiguous fp32 (B, H, Nq) tensors")
+    if last:
+        if out is None:
+            out = torch.empty((B, Nq, H, d), dtype=torch.bfloat16, device=dev)
+        if lse is None:
+            lse = torch.empty((B, H, Nq), dtype=torch.float32, device=dev)
+        if out.dtype != torch.bfloat16 or tuple(out.shape) != (B, Nq, H, d):
+            raise ValueError("dense_attn_fwd_state: `out` must be a bf16 (B, Nq, H, d) view")
+        if lse.dtype != torch.float32 or tuple(lse.shape) != (B, H, Nq) or not lse.is_contiguous():
+            raise ValueError("dense_attn_fwd_state: `lse` must be a contiguous fp32 (B, H, Nq) tensor")
+    lib = _lib.load()
+    with _on(dev):
+        rc = lib.lcbi_dense_attn_fwd_state(_p(q), _p(k), _p(v), _p(out) if last else None, _p(lse) if last else None, B, H,
+                                           Nq, Nk, d, _bnhd_strides(q), _bnhd_strides(k), _bnhd_strides(v),
+                                           _bnhd_strides(out) if last else None, float(scale), _p(st_o), _p(st_m),
+                                           _p(st_l), 1 if first else 0, 1 if last else 0, _stream(dev))
+    _lib.check(rc, "lcbi_dense_attn_fwd_state")
+    return (out, lse) if last else (None, None)
 
 
 def dense_attn_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None, accumulate_dkv=False, accumulate_dq=False):
     """Gradients of dense_attn_fwd. With accumulate_dkv (accumulate_dq), dk/dv (dq) must be fp32 contiguous
     (B,N,H,d) buffers that are accumulated into (ring steps)."""
-    _require_cuda(q, k, v, o, d_o, lse)
+    dev = _require_cuda(q, k, v, o, d_o, lse, dq, dk, dv)
     B, Nq, H, d = q.shape
     Nk = k.shape[1]
-    dev = q.device
-    if accumulate_dq:
-        if dq is None or dq.dtype != torch.float32 or not dq.is_contiguous():
-            raise ValueError("accumulate_dq needs a contiguous fp32 dq accumulator")
-    elif dq is None:
+    for name, t, shape in (("q", q, (B, Nq, H, d)), ("k", k, (B, Nk, H, d)), ("v", v, (B, Nk, H, d)),
+                           ("o", o, (B, Nq, H, d)), ("d_o", d_o, (B, Nq, H, d))):
+        if t.dtype != torch.bfloat16 or tuple(t.shape) != shape:
+            raise ValueError(f"dense_attn_bwd: {name} must be bf16 {shape}, got {t.dtype} {tuple(t.shape)}")
+    if lse.dtype != torch.float32 or tuple(lse.shape) != (B, H, Nq) or not lse.is_contiguous():
+        raise ValueError("dense_attn_bwd: lse must be a contiguous fp32 (B, H, Nq) tensor")
+
+    def _check_grad(name, t, rows, accumulate):
+        want = torch.float32 if accumulate else torch.bfloat16
+        if t.dtype != want or tuple(t.shape) != (B, rows, H, d) or (accumulate and not t.is_contiguous()):
+            raise ValueError(f"dense_attn_bwd: {name} must be a {'contiguous fp32 accumulator' if accumulate else 'bf16 view'} "
+                             f"of shape {(B, rows, H, d)}, got {t.dtype} {tuple(t.shape)}")
+
+    if accumulate_dq and dq is None:
+        raise ValueError("accumulate_dq needs a contiguous fp32 dq accumulator")
+    if accumulate_dkv and (dk is None or dv is None):
+        raise ValueError("accumulate_dkv needs contiguous fp32 dk/dv accumulators")
+    if dq is None:
         dq = torch.empty((B, Nq, H, d), dtype=torch.bfloat16, device=dev)
-    if accumulate_dkv:
-        if dk is None or dv is None or dk.dtype != torch.float32 or not dk.is_contiguous() or not dv.is_contiguous():
-            raise ValueError("accumulate_dkv needs contiguous fp32 dk/dv accumulators")
-    else:
-        if dk is None:
-            dk = torch.empty((B, Nk, H, d), dtype=torch.bfloat16, device=dev)
-        if dv is None:
-            dv = torch.empty((B, Nk, H, d), dtype=torch.bfloat16, device=dev)
+    if dk is None:
+        dk = torch.empty((B, Nk, H, d), dtype=torch.bfloat16, device=dev)
+    if dv is None:
+        dv = torch.empty((B, Nk, H, d), dtype=torch.bfloat16, device=dev)
+    _check_grad("dq", dq, Nq, accumulate_dq)
+    _check_grad("dk", dk, Nk, accumulate_dkv)
+    _check_grad("dv", dv, Nk, accumulate_dkv)
     lib = _lib.load()
-    ws_bytes = lib.lcbi_dense_attn_bwd_workspace_bytes(B, H, Nq, d)
+    ws_bytes = lib.lcbi_dense_attn_bwd_workspace_bytes_for(B, H, Nq, d, 1 if accumulate_dq else 0)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    rc = lib.lcbi_dense_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(dq), _p(dk), _p(dv), B, H, Nq, Nk, d,
-                                 _bnhd_strides(q), _bnhd_strides(k), _bnhd_strides(v), _bnhd_strides(o),
-                                 _bnhd_strides(d_o), _bnhd_strides(dq), _bnhd_strides(dk), _bnhd_strides(dv),
-                                 float(scale), 1 if accumulate_dkv else 0, 1 if accumulate_dq else 0, _p(ws), ws_bytes,
-                                 _stream())
+    with _on(dev):
+        rc = lib.lcbi_dense_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(dq), _p(dk), _p(dv), B, H, Nq, Nk,
+                                     d, _bnhd_strides(q), _bnhd_strides(k), _bnhd_strides(v), _bnhd_strides(o),
+                                     _bnhd_strides(d_o), _bnhd_strides(dq), _bnhd_strides(dk), _bnhd_strides(dv),
+                                     float(scale), 1 if accumulate_dkv else 0, 1 if accumulate_dq else 0, _p(ws),
+                                     ws_bytes, _stream(dev))
     _lib.check(rc, "lcbi_dense_attn_bwd")
     return dq, dk, dv
 
 
 def attn_merge(acc, lse_acc, o_s, lse_s, first, out_bf16=None):
     """Ring-attention combine: merges the partial (o_s, lse_s) into the running fp32 (acc, lse_acc) in place."""
-    _require_cuda(acc, lse_acc, o_s, lse_s)
+    dev = _require_cuda(acc, lse_acc, o_s, lse_s, out_bf16)
     B, N, H, d = acc.shape
     if not (acc.is_contiguous() and o_s.is_contiguous() and lse_acc.is_contiguous() and lse_s.is_contiguous()):
         raise ValueError("attn_merge expects contiguous tensors")
-    rc = _lib.load().lcbi_attn_merge(_p(acc), _p(lse_acc), _p(o_s), _p(lse_s), _p(out_bf16) if out_bf16 is not None else None,
-                                     B, N, H, d, 1 if first else 0, _stream())
+    if acc.dtype != torch.float32 or lse_acc.dtype != torch.float32 or lse_s.dtype != torch.float32:
+        raise ValueError("attn_merge: acc, lse_acc and lse_s must be fp32")
+    if o_s.dtype != torch.bfloat16 or tuple(o_s.shape) != (B, N, H, d):
+        raise ValueError("attn_merge: o_s must be bf16 with acc's shape (B, N, H, d)")
+    if tuple(lse_acc.shape) != (B, H, N) or tuple(lse_s.shape) != (B, H, N):
+        raise ValueError("attn_merge: lse_acc and lse_s must be (B, H, N)")
+    if out_bf16 is not None and (out_bf16.dtype != torch.bfloat16 or tuple(out_bf16.shape) != (B, N, H, d) or
+                                 not out_bf16.is_contiguous()):
+        raise ValueError("attn_merge: out_bf16 must be a contiguous bf16 (B, N, H, d) tensor")
+    with _on(dev):
+        rc = _lib.load().lcbi_attn_merge(_p(acc), _p(lse_acc), _p(o_s), _p(lse_s),
+                                         _p(out_bf16) if out_bf16 is not None else None, B, N, H, d,
+                                         1 if first else 0, _stream(dev))
     _lib.check(rc, "lcbi_attn_merge")
 
 
@@ -157,9 +237,10 @@ class _LayerNorm(torch.autograd.Function):
         y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
         rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
-        rc = _lib.load().lcbi_layer_norm_fwd(_p(x), _is_bf16(x), _p(weight) if weight is not None else None,
-                                             _p(bias) if bias is not None else None, _p(y), _is_bf16(y), _p(mean),
-                                             _p(rstd), rows, C, float(eps), _stream())
+        with _on(x.device):
+            rc = _lib.load().lcbi_layer_norm_fwd(_p(x), _is_bf16(x), _p(weight) if weight is not None else None,
+                                                 _p(bias) if bias is not None else None, _p(y), _is_bf16(y), _p(mean),
+                                                 _p(rstd), rows, C, float(eps), _stream(x.device))
         _lib.check(rc, "lcbi_layer_norm_fwd")
         ctx.save_for_backward(x, weight, mean, rstd)
         ctx.has_bias = bias is not None
@@ -183,11 +264,12 @@ class _LayerNorm(torch.autograd.Function):
             ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
         if need_dx or need_w or need_b:
-            rc = lib.lcbi_layer_norm_bwd(_p(dy), _is_bf16(dy), _p(x), _is_bf16(x),
-                                         _p(weight) if weight is not None else None, _p(mean), _p(rstd),
-                                         _p(dx) if need_dx else None, _p(dw) if need_w else None,
-                                         _p(db) if need_b else None, _p(ws) if ws is not None else None, ws_bytes,
-                                         rows, C, _stream())
+            with _on(x.device):
+                rc = lib.lcbi_layer_norm_bwd(_p(dy), _is_bf16(dy), _p(x), _is_bf16(x),
+                                             _p(weight) if weight is not None else None, _p(mean), _p(rstd),
+                                             _p(dx) if need_dx else None, _p(dw) if need_w else None,
+                                             _p(db) if need_b else None, _p(ws) if ws is not None else None, ws_bytes,
+                                             rows, C, _stream(x.device))
             _lib.check(rc, "lcbi_layer_norm_bwd")
         return dx, dw, db, None, None
 
@@ -196,7 +278,7 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
     """Drop-in for `nn.LayerNorm(C)(x)` as the encoder blocks call it (reference backbone_vit.py:260-263,
     backbone_swin.py:437,489). `out_dtype` defaults to bf16 under bf16 autocast (what the following Linear would cast
     the fp32 result to anyway) and to x.dtype otherwise."""
-    _require_cuda(x)
+    _require_cuda(x, weight, bias)
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     if out_dtype is None:
@@ -226,10 +308,11 @@ class _AddLayerNorm(torch.autograd.Function):
         y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
         rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
-        rc = _lib.load().lcbi_add_layer_norm_fwd(_p(x), _is_bf16(x), _p(delta), _is_bf16(delta), _p(xsum),
-                                                 _p(weight) if weight is not None else None,
-                                                 _p(bias) if bias is not None else None, _p(y), _is_bf16(y), _p(mean),
-                                                 _p(rstd), rows, C, float(eps), _stream())
+        with _on(x.device):
+            rc = _lib.load().lcbi_add_layer_norm_fwd(_p(x), _is_bf16(x), _p(delta), _is_bf16(delta), _p(xsum),
+                                                     _p(weight) if weight is not None else None,
+                                                     _p(bias) if bias is not None else None, _p(y), _is_bf16(y), _p(mean),
+                                                     _p(rstd), rows, C, float(eps), _stream(x.device))
         _lib.check(rc, "lcbi_add_layer_norm_fwd")
         ctx.save_for_backward(xsum, weight, mean, rstd)
         ctx.has_bias = bias is not None
@@ -258,12 +341,13 @@ class _AddLayerNorm(torch.autograd.Function):
         if need_w or need_b:
             ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xsum.device)
-        rc = lib.lcbi_add_layer_norm_bwd(_p(dy), _is_bf16(dy), _p(dxsum) if dxsum is not None else None, _p(xsum),
-                                         _is_bf16(xsum), _p(weight) if weight is not None else None, _p(mean), _p(rstd),
-                                         _p(dx), _p(dd) if dd is not None else None,
-                                         1 if ctx.delta_dtype == torch.bfloat16 else 0, _p(dw) if need_w else None,
-                                         _p(db) if need_b else None, _p(ws) if ws is not None else None, ws_bytes, rows,
-                                         C, _stream())
+        with _on(xsum.device):
+            rc = lib.lcbi_add_layer_norm_bwd(_p(dy), _is_bf16(dy), _p(dxsum) if dxsum is not None else None, _p(xsum),
+                                             _is_bf16(xsum), _p(weight) if weight is not None else None, _p(mean), _p(rstd),
+                                             _p(dx), _p(dd) if dd is not None else None,
+                                             1 if ctx.delta_dtype == torch.bfloat16 else 0, _p(dw) if need_w else None,
+                                             _p(db) if need_b else None, _p(ws) if ws is not None else None, ws_bytes, rows,
+                                             C, _stream(xsum.device))
         _lib.check(rc, "lcbi_add_layer_norm_bwd")
         return (dx if ctx.needs_input_grad[0] else None), dd, dw, db, None, None
 
@@ -272,7 +356,7 @@ def add_layer_norm(x, delta, weight, bias, eps=1e-5, out_dtype=None):
     """`x = x + delta; y = LayerNorm(x)` of a pre-norm block (reference backbone_vit.py:261-262 followed by the next
     norm) as one pass. Returns (x + delta, y). Falls back to the two separate steps for rows of < 128 channels or dtype
     combinations where torch's add would promote away from x's dtype."""
-    _require_cuda(x, delta)
+    _require_cuda(x, delta, weight, bias)
     fusable = (x.dtype in (torch.float32, torch.bfloat16) and delta.dtype in (torch.float32, torch.bfloat16) and
                torch.promote_types(x.dtype, delta.dtype) == x.dtype and x.shape == delta.shape and
                x.shape[-1] % 4 == 0 and x.shape[-1] >= 128 and x.numel() > 0)
@@ -304,7 +388,8 @@ def bias_grad(dy):
     out = torch.empty((C,), dtype=torch.float32, device=dy.device)
     ws_bytes = lib.lcbi_layer_norm_bwd_workspace_bytes(rows, C)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dy.device)
-    rc = lib.lcbi_bias_grad(_p(dy), _is_bf16(dy), _p(out), _p(ws), ws_bytes, rows, C, _stream())
+    with _on(dy.device):
+        rc = lib.lcbi_bias_grad(_p(dy), _is_bf16(dy), _p(out), _p(ws), ws_bytes, rows, C, _stream(dy.device))
     _lib.check(rc, "lcbi_bias_grad")
     return out
 
@@ -369,7 +454,7 @@ class _PatchEmbed(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, img, weight, bias, pos, grid, out_bf16):
-        _require_cuda(img, weight, bias)
+        _require_cuda(img, weight, bias, pos)
         img_c = img.contiguous()
         if img_c.dtype not in (torch.float32, torch.bfloat16):
             img_c = img_c.float()
@@ -382,9 +467,10 @@ class _PatchEmbed(torch.autograd.Function):
         Np = grid3[0] * grid3[1] * grid3[2]
         out = torch.empty((B, Np, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=img.device)
         lib = _lib.load()
-        rc = lib.lcbi_patch_embed_fwd(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(b),
-                                      _p(p) if p is not None else None, _p(out), int(out_bf16), B, Cin,
-                                      _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _stream())
+        with _on(img_c.device):
+            rc = lib.lcbi_patch_embed_fwd(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(b),
+                                          _p(p) if p is not None else None, _p(out), int(out_bf16), B, Cin,
+                                          _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _stream(img_c.device))
         _lib.check(rc, "lcbi_patch_embed_fwd")
         ctx.save_for_backward(img_c, w)
         ctx.geom = (img_dims, patch, grid3, B, Cin, N)
@@ -407,10 +493,11 @@ class _PatchEmbed(torch.autograd.Function):
         dpos = torch.empty((Np, N), dtype=torch.float32, device=dev) if (pos_meta and ctx.needs_input_grad[3]) else None
         dimg = torch.empty(img_c.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
         lib = _lib.load()
-        rc = lib.lcbi_patch_embed_bwd(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(dout),
-                                      int(dout.dtype == torch.bfloat16), _p(dw), _p(db),
-                                      _p(dpos) if dpos is not None else None, _p(dimg) if dimg is not None else None,
-                                      B, Cin, _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _stream())
+        with _on(dev):
+            rc = lib.lcbi_patch_embed_bwd(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(dout),
+                                          int(dout.dtype == torch.bfloat16), _p(dw), _p(db),
+                                          _p(dpos) if dpos is not None else None, _p(dimg) if dimg is not None else None,
+                                          B, Cin, _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _stream(dev))
         _lib.check(rc, "lcbi_patch_embed_bwd")
         return (dimg.to(img_dtype).view(img_shape) if dimg is not None else None, dw.view(w_shape).to(w_dtype),
                 db.to(b_dtype), dpos.view(pos_meta[0]).to(pos_meta[1]) if dpos is not None else None, None, None)
@@ -432,7 +519,7 @@ class _WindowAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qkv, qkv_bias, table, grid, window, shift, scale, win_range=None):
-        _require_cuda(qkv, table)
+        _require_cuda(qkv, qkv_bias, table)
         B, T, _, H, d = qkv.shape
         qkv = qkv.contiguous()
         bias_f = qkv_bias.detach().float().contiguous() if qkv_bias is not None else None
@@ -444,9 +531,10 @@ class _WindowAttention(torch.autograd.Function):
         begin, count = (0, -1) if win_range is None else (int(win_range[0]), int(win_range[1]))
         lib = _lib.load()
         g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
-        rc = lib.lcbi_win_attn_fwd_range(len(grid), g, w, s, B, H, d, float(scale), _p(qkv),
-                                         _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2),
-                                         begin, count, _stream())
+        with _on(qkv.device):
+            rc = lib.lcbi_win_attn_fwd_range(len(grid), g, w, s, B, H, d, float(scale), _p(qkv),
+                                             _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2),
+                                             begin, count, _stream(qkv.device))
         _lib.check(rc, "lcbi_win_attn_fwd_range")
         ctx.save_for_backward(qkv, bias_f, table_f, out, lse2)
         ctx.win_range = (begin, count)
@@ -468,10 +556,11 @@ class _WindowAttention(torch.autograd.Function):
         dtable = torch.zeros_like(table_f)
         lib = _lib.load()
         g, w, s = _lib.int_array(grid), _lib.int_array(window), _lib.int_array(shift)
-        rc = lib.lcbi_win_attn_bwd_range(len(grid), g, w, s, B, H, d, scale, _p(qkv),
-                                         _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2),
-                                         _p(d_out), _p(dsum), _p(dqkv), _p(dbias) if dbias is not None else None,
-                                         _p(dtable), begin, count, _stream())
+        with _on(dev):
+            rc = lib.lcbi_win_attn_bwd_range(len(grid), g, w, s, B, H, d, scale, _p(qkv),
+                                             _p(bias_f) if bias_f is not None else None, _p(table_f), _p(out), _p(lse2),
+                                             _p(d_out), _p(dsum), _p(dqkv), _p(dbias) if dbias is not None else None,
+                                             _p(dtable), begin, count, _stream(dev))
         _lib.check(rc, "lcbi_win_attn_bwd_range")
         bias_dtype, table_dtype = ctx.meta
         return (dqkv, dbias.to(bias_dtype) if dbias is not None else None, dtable.to(table_dtype), None, None, None, None,
@@ -519,7 +608,8 @@ def window_maps(grid, window, shift, device="cuda"):
     gather = torch.empty((nw.value, n.value), dtype=torch.int32, device=device)
     region = torch.empty((nw.value, n.value), dtype=torch.int32, device=device)
     relidx = torch.empty((n.value, n.value), dtype=torch.int32, device=device)
-    rc = lib.lcbi_window_maps(len(grid), g, w, s, _p(gather), _p(region), _p(relidx), ctypes.byref(n), ctypes.byref(nw),
-                              _stream())
+    with _on(gather.device):
+        rc = lib.lcbi_window_maps(len(grid), g, w, s, _p(gather), _p(region), _p(relidx), ctypes.byref(n), ctypes.byref(nw),
+                                  _stream(gather.device))
     _lib.check(rc, "lcbi_window_maps")
     return gather, region, relidx

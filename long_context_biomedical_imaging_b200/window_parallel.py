@@ -1,24 +1,36 @@
-"""Window-sharded Swin attention over torch.distributed (SURVEY.md 8e, row "Swin windows").
+"""Window-sharded Swin attention over torch.distributed (SURVEY.md 8e, row "Swin windows", option (a)).
 
 The windows of one W-MSA / SW-MSA block are independent, so the flattened (batch, window) list is split evenly over
-the ranks of a process group: every rank holds the full (replicated) qkv of the block, runs the fused kernel on its
-window range only (`ops.window_attention(..., win_range=...)`, C ABI `lcbi_win_attn_{fwd,bwd}_range`) and the
-per-rank outputs - disjoint token rows, zeros elsewhere - are summed with one all-reduce. Backward mirrors it: the
-incoming gradient is replicated, every rank back-propagates through its windows, and the gradients of the replicated
-inputs (qkv, qkv.bias, the relative-position table) are summed over the ranks. Consecutive blocks use different
-(shifted) partitions, so tokens must be visible to every rank between blocks: this is the simple formulation of 8e
-(a); per-GPU compute at cfg4 stage 1 is a few hundred microseconds, so the all-reduces (25 MB forward, 75 MB
-backward) and not the kernels bound this configuration - bench.py --workload cfg4 reports it as measured.
+the ranks of a process group: every rank holds the full (replicated) qkv of the block and runs the fused kernel on its
+window range only (`ops.window_attention(..., win_range=...)`, C ABI `lcbi_win_attn_{fwd,bwd}_range`). Every token
+belongs to exactly one window, so the ranks' results are DISJOINT token rows: they are exchanged with ONE all-gather of
+the owned rows (window-major, 1/P of the tensor per rank) followed by a scatter to token order — not an all-reduce of
+the zero-padded full tensor, which moves twice the bytes. Backward mirrors it: the incoming gradient is replicated,
+every rank back-propagates through its windows, the dqkv rows (disjoint again) are all-gathered, and the two small
+parameter gradients (qkv.bias through the pad tokens, the relative-position table) share one all-reduce.
+
+Consecutive blocks use different (shifted) partitions, so tokens must be visible to every rank between blocks: this is
+the simple formulation of 8e (a). Per-GPU compute at cfg4 stage 1 is of the order of 100 microseconds, so collective
+latency and not the kernels bounds this configuration - bench.py reports it as measured.
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def _used_window(grid, window, shift):
+    """Reference get_window_size clamp (backbone_swin.py:200-224)."""
+    win = [int(g) if g <= w else int(w) for g, w in zip(grid, window)]
+    sh = [0 if g <= w else int(s) for g, w, s in zip(grid, window, shift)]
+    return win, sh
 
 
 def count_windows(grid, window):
-    """Windows per image for a token grid and a CONSTRUCTOR window (reference get_window_size clamp,
-    backbone_swin.py:200-224, then ceil division of the padded grid)."""
+    """Windows per image for a token grid and a CONSTRUCTOR window (clamp, then ceil division of the padded grid)."""
     total = 1
     for g, w in zip(grid, window):
         w_used = g if g <= w else w
@@ -33,8 +45,86 @@ def shard_range(total, world, rank):
     return begin, min(per, total - begin)
 
 
+@functools.lru_cache(maxsize=64)
+def _window_token_ids(grid, window, shift):
+    """(nW, n) int64 on the CPU: token index (raster order of the un-padded grid) feeding each window slot, -1 for the
+    zero-pad tokens — the reference's pad -> roll(-shift) -> window_partition chain (backbone_swin.py:441-468) applied
+    to an index tensor."""
+    win, sh = _used_window(grid, window, shift)
+    t = 1
+    for g in grid:
+        t *= g
+    ids = torch.arange(t, dtype=torch.int64).reshape(grid)
+    pads = []
+    for g, w in zip(reversed(grid), reversed(win)):
+        pads += [0, (w - g % w) % w]
+    ids = F.pad(ids, pads, value=-1)
+    if any(s > 0 for s in sh):
+        ids = torch.roll(ids, shifts=[-s for s in sh], dims=list(range(len(grid))))
+    k = len(grid)
+    nwin = [p // w for p, w in zip(ids.shape, win)]
+    shape = []
+    for a, b in zip(nwin, win):
+        shape += [a, b]
+    ids = ids.reshape(shape).permute(*range(0, 2 * k, 2), *range(1, 2 * k, 2))
+    n = 1
+    for w in win:
+        n *= w
+    return ids.reshape(-1, n).contiguous()
+
+
+def _row_ids(batch, grid, window, shift, world, device):
+    """Flattened (batch*T) token row of every slot of every rank's window range, padded to `per` windows per rank:
+    (world, per*n) int64, -1 for pad tokens and for the dummy windows that even out the last ranks."""
+    ids = _window_token_ids(tuple(grid), tuple(window), tuple(shift))            # (nW, n)
+    nW, n = ids.shape
+    t = 1
+    for g in grid:
+        t *= g
+    full = torch.cat([torch.where(ids >= 0, ids + b * t, ids) for b in range(batch)], 0)      # (B*nW, n)
+    per = -(-(batch * nW) // world)
+    padded = torch.full((world * per, n), -1, dtype=torch.int64)
+    padded[:batch * nW] = full
+    return padded.reshape(world, per * n).to(device), batch * t
+
+
+def _all_gather_rows(rows, group, world):
+    out = rows.new_empty((world * rows.shape[0],) + tuple(rows.shape[1:]))
+    try:
+        dist.all_gather_into_tensor(out, rows, group=group)
+    except (RuntimeError, NotImplementedError):          # a backend without the flat variant
+        dist.all_gather(list(out.chunk(world, 0)), rows, group=group)
+    return out
+
+
+def _exchange_disjoint_rows(x2d, ids, n_rows, rank, group, world):
+    """x2d: (n_rows, F) whose rows owned by this rank (ids[rank]) are valid. Returns the (n_rows, F) tensor in which
+    every rank's owned rows are filled in: gather own rows -> all-gather -> scatter by token id."""
+    mine = x2d.index_select(0, ids[rank].clamp(min=0))
+    everyone = _all_gather_rows(mine.contiguous(), group, world)
+    flat_ids = ids.reshape(-1)
+    out = x2d.new_empty((n_rows + 1, x2d.shape[1]))                       # last row swallows pad / dummy slots
+    out.index_copy_(0, torch.where(flat_ids >= 0, flat_ids, torch.full_like(flat_ids, n_rows)), everyone)
+    return out[:n_rows]
+
+
+class _ReplicatedRows(torch.autograd.Function):
+    """Identity on the replicated qkv; the gradient rows each rank produced (those of its windows) are all-gathered."""
+
+    @staticmethod
+    def forward(ctx, x, ids, n_rows, rank, group, world):
+        ctx.meta = (ids, n_rows, rank, group, world)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, n_rows, rank, group, world = ctx.meta
+        full = _exchange_disjoint_rows(g.reshape(n_rows, g.shape[-1]), ids, n_rows, rank, group, world)
+        return full.reshape(g.shape), None, None, None, None, None
+
+
 class _ReplicatedInput(torch.autograd.Function):
-    """Identity on a tensor every rank holds a copy of; its gradient is the sum of the ranks' partial gradients."""
+    """Identity on a small tensor every rank holds a copy of; its gradient is the sum of the ranks' partial gradients."""
 
     @staticmethod
     def forward(ctx, x, group):
@@ -48,18 +138,18 @@ class _ReplicatedInput(torch.autograd.Function):
         return g, None
 
 
-class _SumOutputs(torch.autograd.Function):
-    """Sum of the ranks' partial outputs (disjoint rows); the incoming gradient is already replicated."""
+class _GatherOutputs(torch.autograd.Function):
+    """Partial output (own windows' rows valid) -> full output on every rank. The incoming gradient is replicated and
+    the range backward reads only its own windows' rows of it, so it is passed through unchanged."""
 
     @staticmethod
-    def forward(ctx, x, group):
-        x = x.contiguous().clone()
-        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
-        return x
+    def forward(ctx, part, ids, n_rows, rank, group, world):
+        full = _exchange_disjoint_rows(part.reshape(n_rows, part.shape[-1]), ids, n_rows, rank, group, world)
+        return full.reshape(part.shape)
 
     @staticmethod
     def backward(ctx, g):
-        return g, None
+        return g, None, None, None, None, None
 
 
 def window_attention_sharded(qkv, qkv_bias, table, grid, window, shift, num_heads, scale=None, group=None, attn_fn=None):
@@ -72,10 +162,17 @@ def window_attention_sharded(qkv, qkv_bias, table, grid, window, shift, num_head
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return attn_fn(qkv, qkv_bias, table, grid, window, shift, num_heads, scale)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    total = qkv.shape[0] * count_windows(grid, window)
+    grid = tuple(int(g) for g in grid)
+    batch = qkv.shape[0]
+    total = batch * count_windows(grid, window)
     begin, count = shard_range(total, world, rank)
-    qkv_r = _ReplicatedInput.apply(qkv, group)
-    bias_r = _ReplicatedInput.apply(qkv_bias, group) if qkv_bias is not None else None
-    table_r = _ReplicatedInput.apply(table, group)
+    ids, n_rows = _row_ids(batch, grid, tuple(int(w) for w in window), tuple(int(s) for s in shift), world, qkv.device)
+    qkv_r = _ReplicatedRows.apply(qkv, ids, n_rows, rank, group, world)
+    if qkv_bias is not None:                 # one all-reduce for both small parameter gradients
+        packed = _ReplicatedInput.apply(torch.cat([qkv_bias.reshape(-1), table.reshape(-1).to(qkv_bias.dtype)]), group)
+        bias_r = packed[:qkv_bias.numel()].reshape(qkv_bias.shape)
+        table_r = packed[qkv_bias.numel():].reshape(table.shape).to(table.dtype)
+    else:
+        bias_r, table_r = None, _ReplicatedInput.apply(table, group)
     part = attn_fn(qkv_r, bias_r, table_r, grid, window, shift, num_heads, scale, win_range=(begin, count))
-    return _SumOutputs.apply(part, group)
+    return _GatherOutputs.apply(part, ids, n_rows, rank, group, world)

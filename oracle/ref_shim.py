@@ -9,9 +9,11 @@ their published semantics are restated below as stubs (strided conv + flatten/tr
 position embedding; trailing zero-pad + strided conv; linear1 -> GELU -> linear2), which is all the
 reference's call sites (`backbone_vit.py:351-361,383`, `backbone_swin.py:800-806,885,433`) rely on.
 
-This module only works where /root/reference exists (the build container). It is used by
-`oracle/make_golden.py` to generate the committed fixtures under tests/golden/ and by CPU tests that are
-skipped when the reference tree is absent (the GPU box).
+This module only works where the reference's files exist: /root/reference in the build container, or the copy of
+the four model files (`model/models/backbone_{vit,swin}.py`, `hyena.py`, `mamba.py`) that `__graft_entry__.build()`
+stages under the git-ignored `baseline/_ref/` so that `bench.py --impl reference` can time the reference's OWN
+attention code on the GPU box's host cores. It is used by `oracle/make_golden.py` to generate the committed fixtures
+under tests/golden/ and by CPU tests that are skipped when no reference tree is present.
 """
 from __future__ import annotations
 
@@ -24,7 +26,37 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("LCBI_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO_ROOT, "baseline", "_ref")
+STAGED_FILES = ("backbone_vit.py", "backbone_swin.py", "hyena.py", "mamba.py")
+
+
+def _pick_root():
+    env = os.environ.get("LCBI_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", STAGED_ROOT):
+        if os.path.isfile(os.path.join(root, "model", "models", "backbone_swin.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def stage_reference_files(src_root="/root/reference"):
+    """Copies the four reference model files into baseline/_ref/ (git-ignored, travels to the GPU box). Returns the
+    staged root, or None when the source tree is absent. Called by __graft_entry__.build() in the build container."""
+    import shutil
+
+    src_dir = os.path.join(src_root, "model", "models")
+    if not all(os.path.isfile(os.path.join(src_dir, f)) for f in STAGED_FILES):
+        return None
+    dst_dir = os.path.join(STAGED_ROOT, "model", "models")
+    os.makedirs(dst_dir, exist_ok=True)
+    for f in STAGED_FILES:
+        shutil.copyfile(os.path.join(src_dir, f), os.path.join(dst_dir, f))
+    return STAGED_ROOT
 
 
 def reference_available() -> bool:

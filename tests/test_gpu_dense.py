@@ -21,7 +21,7 @@ def _t(a, dev="cuda"):
 
 
 @pytest.mark.parametrize("B,H,N", [(2, 3, 196), (2, 3, 197), (1, 2, 128), (1, 1, 1), (1, 2, 129), (1, 12, 1728),
-                                   (3, 2, 640)])
+                                   (3, 2, 640), (4, 12, 1728), (1, 12, 8192)])   # SURVEY Appendix C dense matrix
 def test_dense_attention_core_vs_oracle(B, H, N):
     from long_context_biomedical_imaging_b200 import ops
 
@@ -283,3 +283,122 @@ def test_dense_backward_full_size_properties():
     scale_ref = float(dq.float().abs().max())            # gradient magnitude of the generic case
     assert float(dq2.float().abs().max()) < 2e-2 * scale_ref
     assert float(dk2.float().abs().max()) < 2e-2 * float(dk.float().abs().max())
+
+
+def test_dense_forward_with_carried_state_equals_one_pass():
+    """lcbi_dense_attn_fwd_state: folding the K/V sequence in 3 ragged shards through the carried (m, l, O) state gives
+    the result of one pass over all keys (same kernel arithmetic; lse to fp32 rounding, o to one bf16 ulp)."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(11)
+    B, H, Nq, d = 2, 3, 333, 64
+    cuts = [0, 200, 264, 777]
+    q = torch.randn(B, Nq, H, d, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, cuts[-1], H, d, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, cuts[-1], H, d, device="cuda").to(torch.bfloat16)
+    k[:, 300:] *= 3.0                       # later shards raise the running max: the rescale path runs
+    o_ref, lse_ref = ops.dense_attn_fwd(q, k, v, 0.125)
+    state = (torch.empty(B, Nq, H, d, device="cuda"), torch.empty(B, H, Nq, device="cuda"),
+             torch.empty(B, H, Nq, device="cuda"))
+    out = lse = None
+    for i in range(3):
+        ks, vs = k[:, cuts[i]:cuts[i + 1]], v[:, cuts[i]:cuts[i + 1]]
+        out, lse = ops.dense_attn_fwd_state(q, ks, vs, 0.125, state, first=i == 0, last=i == 2)
+    assert max_rel(lse.cpu(), lse_ref.cpu()) < 1e-5
+    assert max_rel(out.float().cpu(), o_ref.float().cpu()) < 1e-2
+    qf, kf, vf = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+    ref = ao.dense_attention(qf, kf, vf, 0.125).permute(0, 2, 1, 3)
+    assert max_rel(out.float().cpu(), ref.cpu()) < BF16_TOL
+
+
+def test_dense_rejects_operands_on_mixed_devices_and_bad_dtypes():
+    from long_context_biomedical_imaging_b200 import ops
+
+    q, k, v = [torch.randn(1, 64, 1, 64, device="cuda").to(torch.bfloat16) for _ in range(3)]
+    o, lse = ops.dense_attn_fwd(q, k, v, 0.125)
+    with pytest.raises(ValueError):          # fp32 `o` (e.g. a ring accumulator passed by mistake)
+        ops.dense_attn_bwd(q, k, v, o.float(), torch.randn_like(o), lse, 0.125)
+    with pytest.raises(ValueError):          # bf16 dk with accumulate_dkv
+        ops.dense_attn_bwd(q, k, v, o, torch.randn_like(o), lse, 0.125, dk=torch.zeros_like(k), dv=torch.zeros_like(v),
+                           accumulate_dkv=True)
+    with pytest.raises(ValueError):
+        ops.attn_merge(torch.zeros(1, 64, 1, 64, device="cuda"), lse.clone(), o.float(), lse, True)
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(ValueError):
+            ops.dense_attn_fwd(q, k.to("cuda:1"), v, 0.125)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_ops_run_on_the_operands_device_not_the_current_one():
+    """a model on cuda:1 while the process default is cuda:0 must launch on cuda:1's stream."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.cuda.set_device(0)
+    torch.manual_seed(3)
+    q, k, v = [torch.randn(1, 200, 2, 64, device="cuda:1").to(torch.bfloat16) for _ in range(3)]
+    o, lse = ops.dense_attn_fwd(q, k, v, 0.125)
+    assert o.device == q.device and torch.cuda.current_device() == 0
+    qf, kf, vf = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+    ref = ao.dense_attention(qf, kf, vf, 0.125).permute(0, 2, 1, 3)
+    assert max_rel(o.float().cpu(), ref.cpu()) < BF16_TOL
+
+
+def test_sablock_under_fp16_autocast_with_grad_scaler():
+    """What the unmodified reference harness selects on a B200 (utils/status.py:50-58 does not list it as bf16-capable:
+    fp16 autocast + GradScaler, trainer_base.py:116,166-171). The kernels compute in bf16 (fp16 qkv is cast), gradients
+    arrive scaled by the GradScaler's factor and are un-scaled by it: results must match the fp32 reference."""
+    from long_context_biomedical_imaging_b200.backbone_vit import SABlock
+
+    g = load_golden("sablock.npz")
+    H = int(g["a/heads"])
+    C = g["a/x"].shape[-1]
+    blk = SABlock(False, False, C, H).cuda()
+    with torch.no_grad():
+        blk.qkv.weight.copy_(_t(g["a/w_qkv"]))
+        blk.out_proj.weight.copy_(_t(g["a/w_out"]))
+        blk.out_proj.bias.copy_(_t(g["a/b_out"]))
+    x = _t(g["a/x"]).requires_grad_(True)
+    opt = torch.optim.SGD(blk.parameters(), lr=0.0)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = blk(x)
+    loss = (y.float() * _t(g["a/dout"])).sum()
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    assert max_rel(y.detach().float().cpu(), g["a/y"]) < BF16_TOL
+    assert max_rel(x.grad.cpu() / 1024.0, g["a/dx"]) < BF16_TOL          # x is not an optimizer parameter: still scaled
+    assert max_rel(blk.qkv.weight.grad.cpu(), g["a/dw_qkv"]) < BF16_TOL
+    assert max_rel(blk.out_proj.weight.grad.cpu(), g["a/dw_out"]) < BF16_TOL
+    assert max_rel(blk.out_proj.bias.grad.cpu(), g["a/db_out"]) < BF16_TOL
+
+
+def test_vit_encoder_under_ddp_without_unused_parameters():
+    """trainer_base.py:94-98 wraps the model in DDP(find_unused_parameters=False): every parameter must receive a
+    gradient in every step or the reducer raises on the next forward. One-process NCCL group, two steps."""
+    import os
+    import socket
+
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from long_context_biomedical_imaging_b200.backbone_vit import custom_ViT
+
+    cfg = types.SimpleNamespace(ViT=types.SimpleNamespace(size="custom", hidden_size=128, mlp_dim=256, num_layers=2,
+                                                          num_heads=2, patch_size=[1, 8, 8], use_hyena=False,
+                                                          use_mamba=False),
+                                time=1, height=32, width=32, task_type="class")
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        model, _ = custom_ViT(cfg, 1)
+        ddp = DDP(model.cuda(), find_unused_parameters=False)
+        for _ in range(2):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                outs = ddp(torch.randn(2, 1, 1, 32, 32, device="cuda"))
+            sum(o.float().sum() for o in outs[1:]).backward()
+        assert all(p.grad is not None for p in model.parameters())
+    finally:
+        dist.destroy_process_group()

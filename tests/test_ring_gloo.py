@@ -1,5 +1,6 @@
-"""CPU, world_size 2 and 3 over gloo: the ring (sequence-parallel) attention driver — K/V rotation, log-sum-exp
-merging, travelling dK/dV accumulators — with the attention math supplied by the oracle instead of the CUDA kernels.
+"""CPU, world_size 2 and 3 over gloo: the ring (sequence-parallel) attention driver — K/V rotation, the online-softmax
+state carried from step to step, travelling dK/dV sums added on arrival — with the attention math supplied by the
+oracle instead of the CUDA kernels.
 The result must equal single-process global attention (forward and all gradients)."""
 import os
 import socket
@@ -25,16 +26,28 @@ def _fwd(q, k, v, scale):
     return ao.dense_attention(qh, kh, vh, scale).permute(0, 2, 1, 3).contiguous(), lse
 
 
-def _merge(acc, lse_acc, o_s, lse_s, first):
+def _fwd_state(q, k, v, scale, state, first, last, out, lse):
+    """CPU stand-in for lcbi_dense_attn_fwd_state: same contract (state = un-normalised output, running max in raw score
+    units, running sum; `last` normalises into out / lse)."""
+    st_o, st_m, st_l = state
+    qh, kh, vh = [t.permute(0, 2, 1, 3) for t in (q, k, v)]
+    s = torch.einsum("bhxd,bhyd->bhxy", qh, kh)                      # raw scores (B,H,Nq,Nk)
+    m_new = s.max(-1).values
+    if not first:
+        m_new = torch.maximum(m_new, st_m)
+    p = torch.exp((s - m_new.unsqueeze(-1)) * scale)
+    o_part = torch.einsum("bhxy,bhyd->bhxd", p, vh).permute(0, 2, 1, 3)
     if first:
-        acc.copy_(o_s)
-        lse_acc.copy_(lse_s)
-        return
-    new = torch.logaddexp(lse_acc, lse_s)
-    wa = torch.exp(lse_acc - new).permute(0, 2, 1).unsqueeze(-1)
-    ws = torch.exp(lse_s - new).permute(0, 2, 1).unsqueeze(-1)
-    acc.copy_(acc * wa + o_s * ws)
-    lse_acc.copy_(new)
+        st_o.copy_(o_part)
+        st_l.copy_(p.sum(-1))
+    else:
+        alpha = torch.exp((st_m - m_new) * scale)
+        st_o.copy_(st_o * alpha.permute(0, 2, 1).unsqueeze(-1) + o_part)
+        st_l.copy_(st_l * alpha + p.sum(-1))
+    st_m.copy_(m_new)
+    if last:
+        out.copy_(st_o / st_l.permute(0, 2, 1).unsqueeze(-1))
+        lse.copy_(st_m * scale + torch.log(st_l))
 
 
 def _bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv):
@@ -61,7 +74,7 @@ def _worker(rank, world, port, n_local, result_queue):
         sl = slice(rank * n_local, (rank + 1) * n_local)
         comm = ring.RingComm()
         assert comm.world == world
-        acc, lse = ring.ring_attention_forward(q[:, sl], k[:, sl], v[:, sl], 0.3, comm, fwd_fn=_fwd, merge_fn=_merge)
+        acc, lse = ring.ring_attention_forward(q[:, sl], k[:, sl], v[:, sl], 0.3, comm, fwd_state_fn=_fwd_state)
         dq, dk, dv = ring.ring_attention_backward(q[:, sl], k[:, sl], v[:, sl], acc, d_o[:, sl], lse, 0.3, comm,
                                                   bwd_fn=_bwd)
         # single-process reference
@@ -102,7 +115,7 @@ def test_ring_single_rank_degenerates_to_one_step():
 
         torch.manual_seed(1)
         q, k, v = [torch.randn(1, 7, 2, 8) for _ in range(3)]
-        acc, lse = ring.ring_attention_forward(q, k, v, 0.5, ring.RingComm(), fwd_fn=_fwd, merge_fn=_merge)
+        acc, lse = ring.ring_attention_forward(q, k, v, 0.5, ring.RingComm(), fwd_state_fn=_fwd_state)
         ref, ref_lse = _fwd(q, k, v, 0.5)
         assert torch.allclose(acc, ref, atol=1e-6) and torch.allclose(lse, ref_lse, atol=1e-6)
     finally:

@@ -1,5 +1,5 @@
-"""CPU, world_size 2 and 3 over gloo: the window-sharded Swin attention driver (range split, output all-reduce,
-gradient all-reduce of the replicated inputs) with the attention math supplied by the oracle instead of the CUDA
+"""CPU, world_size 2 and 3 over gloo: the window-sharded Swin attention driver (range split, all-gather of the owned
+output / dqkv rows, one all-reduce for the small parameter gradients) with the attention math supplied by the oracle instead of the CUDA
 kernels. Every rank must end up with the single-process result, forward and all gradients."""
 import os
 import socket
@@ -49,7 +49,8 @@ def _worker(rank, world, port, queue):
         out = wp.window_attention_sharded(qkv, bias, table, c["grid"], c["window"], c["shift"], c["heads"],
                                           attn_fn=ao.window_attention_core)
         out.backward(d_out)
-        queue.put((rank, out.detach(), qkv.grad, bias.grad, table.grad))
+        # numpy arrays are pickled by value: a tensor would travel as a shared-memory handle that dies with this process
+        queue.put((rank, out.detach().numpy(), qkv.grad.numpy(), bias.grad.numpy(), table.grad.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -72,7 +73,8 @@ def test_window_sharded_attention_equals_single_process(world):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, out, dqkv, dbias, dtable in results:
+    for rank, *arrays in results:
+        out, dqkv, dbias, dtable = [torch.from_numpy(a) for a in arrays]
         torch.testing.assert_close(out, want.detach(), rtol=1e-10, atol=1e-10)
         torch.testing.assert_close(dqkv, qkv.grad, rtol=1e-9, atol=1e-10)
         torch.testing.assert_close(dbias, bias.grad, rtol=1e-9, atol=1e-10)
