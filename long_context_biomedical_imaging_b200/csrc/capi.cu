@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "lcbi_kernels.h"
+#include "tma_host.h"
 
 namespace lcbi {
 
@@ -20,6 +21,10 @@ int set_cuda_error(cudaError_t e) {
 }
 
 static int fail(int code, const char* msg) {
+  if (code == LCBI_ERR_TENSOR_MAP) {       // name the rejected view
+    std::snprintf(g_err, sizeof(g_err), "%s [%s]", msg, tmap_error_text());
+    return code;
+  }
   set_error_text(msg);
   return code;
 }

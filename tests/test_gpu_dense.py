@@ -402,3 +402,21 @@ def test_vit_encoder_under_ddp_without_unused_parameters():
         assert all(p.grad is not None for p in model.parameters())
     finally:
         dist.destroy_process_group()
+
+
+def test_backward_as_first_cuda_call_of_the_autograd_thread():
+    """The TMA tensor maps are encoded through the driver API, which needs a context bound to the calling thread. When
+    the attention backward is the FIRST node autograd's worker thread executes, that thread has made no runtime call yet
+    (found by bench.py's parity_check in round 2: CUDA_ERROR_INVALID_CONTEXT); the library binds the context and retries.
+    Run in a fresh interpreter so that the worker thread is new."""
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from long_context_biomedical_imaging_b200 import ops\n"
+        "x = torch.randn(1, 256, 3 * 128, device='cuda').to(torch.bfloat16).requires_grad_(True)\n"
+        "ops.dense_attention_qkv(x, 2).backward(torch.ones(1, 256, 128, device='cuda', dtype=torch.bfloat16))\n"
+        "torch.cuda.synchronize(); assert x.grad is not None; print('ok')\n" % __import__("conftest").ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
