@@ -73,9 +73,27 @@ def _window_token_ids(grid, window, shift):
     return ids.reshape(-1, n).contiguous()
 
 
+_ROW_ID_CACHE = {}
+
+
 def _row_ids(batch, grid, window, shift, world, device):
-    """Flattened (batch*T) token row of every slot of every rank's window range, padded to `per` windows per rank:
-    (world, per*n) int64, -1 for pad tokens and for the dummy windows that even out the last ranks."""
+    """Cached on the device per geometry (built once: the map is static for a block):
+      gather_ids  (world, per*n) int64  flattened (batch*T) token row of every slot of every rank's window range, padded
+                  to `per` windows per rank; pad tokens and the dummy windows that even out the last ranks read row 0
+      scatter_ids (world*per*n) int64   the same, with those slots pointing at a dump row (index batch*T)."""
+    key = (batch, tuple(grid), tuple(window), tuple(shift), world, str(device))
+    hit = _ROW_ID_CACHE.get(key)
+    if hit is None:
+        ids, n_rows = _build_row_ids(batch, grid, window, shift, world)
+        flat = ids.reshape(-1)
+        hit = (ids.clamp(min=0).to(device), torch.where(flat >= 0, flat, torch.full_like(flat, n_rows)).to(device), n_rows)
+        if len(_ROW_ID_CACHE) > 64:
+            _ROW_ID_CACHE.clear()
+        _ROW_ID_CACHE[key] = hit
+    return hit
+
+
+def _build_row_ids(batch, grid, window, shift, world):
     ids = _window_token_ids(tuple(grid), tuple(window), tuple(shift))            # (nW, n)
     nW, n = ids.shape
     t = 1
@@ -85,7 +103,7 @@ def _row_ids(batch, grid, window, shift, world, device):
     per = -(-(batch * nW) // world)
     padded = torch.full((world * per, n), -1, dtype=torch.int64)
     padded[:batch * nW] = full
-    return padded.reshape(world, per * n).to(device), batch * t
+    return padded.reshape(world, per * n), batch * t
 
 
 def _all_gather_rows(rows, group, world):
@@ -98,13 +116,13 @@ def _all_gather_rows(rows, group, world):
 
 
 def _exchange_disjoint_rows(x2d, ids, n_rows, rank, group, world):
-    """x2d: (n_rows, F) whose rows owned by this rank (ids[rank]) are valid. Returns the (n_rows, F) tensor in which
-    every rank's owned rows are filled in: gather own rows -> all-gather -> scatter by token id."""
-    mine = x2d.index_select(0, ids[rank].clamp(min=0))
-    everyone = _all_gather_rows(mine.contiguous(), group, world)
-    flat_ids = ids.reshape(-1)
+    """x2d: (n_rows, F) whose rows owned by this rank are valid. Returns the (n_rows, F) tensor in which every rank's
+    owned rows are filled in: gather own rows -> all-gather -> scatter by token id. ids = (gather_ids, scatter_ids)."""
+    gather_ids, scatter_ids = ids
+    mine = x2d.index_select(0, gather_ids[rank])
+    everyone = _all_gather_rows(mine, group, world)
     out = x2d.new_empty((n_rows + 1, x2d.shape[1]))                       # last row swallows pad / dummy slots
-    out.index_copy_(0, torch.where(flat_ids >= 0, flat_ids, torch.full_like(flat_ids, n_rows)), everyone)
+    out.index_copy_(0, scatter_ids, everyone)
     return out[:n_rows]
 
 
@@ -166,7 +184,9 @@ def window_attention_sharded(qkv, qkv_bias, table, grid, window, shift, num_head
     batch = qkv.shape[0]
     total = batch * count_windows(grid, window)
     begin, count = shard_range(total, world, rank)
-    ids, n_rows = _row_ids(batch, grid, tuple(int(w) for w in window), tuple(int(s) for s in shift), world, qkv.device)
+    g_ids, s_ids, n_rows = _row_ids(batch, grid, tuple(int(w) for w in window), tuple(int(s) for s in shift), world,
+                                    qkv.device)
+    ids = (g_ids, s_ids)
     qkv_r = _ReplicatedRows.apply(qkv, ids, n_rows, rank, group, world)
     if qkv_bias is not None:                 # one all-reduce for both small parameter gradients
         packed = _ReplicatedInput.apply(torch.cat([qkv_bias.reshape(-1), table.reshape(-1).to(qkv_bias.dtype)]), group)
