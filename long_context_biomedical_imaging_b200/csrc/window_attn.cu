@@ -28,6 +28,9 @@ namespace lcbi {
 
 int win_attn_fwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream);   // window_attn_small.cu
 int win_attn_bwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream);   // window_attn_small.cu
+bool win_attn_tc_applicable(const WinParams& p, int head_dim);                           // window_attn_tc.cu
+int win_attn_fwd_tc_launch(const WinParams& p, int head_dim, cudaStream_t stream);       // window_attn_tc.cu
+int win_attn_bwd_tc_launch(const WinParams& p, int head_dim, cudaStream_t stream);       // window_attn_tc.cu
 
 namespace {
 
@@ -863,6 +866,8 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
   // CTA-per-(window, head) kernel below fills the machine better (measured).
   static const bool legacy_small_fwd = std::getenv("LCBI_WIN_LEGACY_FWD") != nullptr;
   if (p.g.n <= 64 && p.win_count >= 1024 && !legacy_small_fwd) return win_attn_fwd_small_launch(p, a.head_dim, stream);
+  // 3-D windows of 128..512 tokens (7^3, 8^3): tcgen05 / TMEM kernel fed by TMA box / gather4 loads (window_attn_tc.cu)
+  if (win_attn_tc_applicable(p, a.head_dim)) return win_attn_fwd_tc_launch(p, a.head_dim, stream);
   const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
   dim3 grid(p.win_count, p.H);
   if (a.head_dim == 16) {
@@ -902,6 +907,13 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
   // small windows (<= 64 tokens): one fused kernel produces dq, dk, dv, the pad-token bias gradient and d(table)
   static const bool legacy_small_bwd = std::getenv("LCBI_WIN_LEGACY_BWD") != nullptr;
   if (p.g.n <= 64 && !legacy_small_bwd) return win_attn_bwd_small_launch(p, D, stream);
+  // 3-D windows of 128..512 tokens: ONE tcgen05 kernel produces dq, dk, dv, the pad-token bias gradient and d(table) with
+  // a single recompute of S (window_attn_tc.cu); shapes whose operands do not fit its shared memory fall through
+  static const bool no_tc_bwd = std::getenv("LCBI_WIN_NO_TC_BWD") != nullptr;
+  if (!no_tc_bwd && win_attn_tc_applicable(p, D)) {
+    rc = win_attn_bwd_tc_launch(p, D, stream);
+    if (rc != LCBI_ERR_UNSUPPORTED) return rc;
+  }
   // 2. dK, dV (+ pad-token bias gradient)
   {
     const size_t smem = dkdv_smem_bytes(p.g, D);
