@@ -140,6 +140,11 @@ int lcbi_win_attn_bwd(int ndim, const int* grid, const int* window, const int* s
                       const float* lse2, const void* d_out, float* dsum, void* dqkv, float* dbias_pad, float* dtable,
                       void* stream);
 
+/* Which kernels serve 3-D windows of 128..512 tokens: 0 = automatic (by measured crossover: the tcgen05 / TMEM / TMA
+ * kernels of window_attn_tc.cu where they are at least as fast as the generic mma.sync kernels), 1 = tcgen05 wherever
+ * applicable, 2 = generic only. Process-wide; for tests and A/B timing. */
+int lcbi_set_window_kernel_mode(int mode);
+
 /* Window-sharded variants (the windows of one block are independent, so the flattened (batch, window) list
  * can be split across GPUs): only windows [win_begin, win_begin + win_count) are processed (win_count < 0: all).
  * Forward writes `out` / `lse2` rows of the tokens inside those windows only; backward writes the matching `dqkv` rows

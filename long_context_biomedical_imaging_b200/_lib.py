@@ -59,6 +59,7 @@ SIGNATURES = {
                                                ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64,
                                                ctypes.c_int, c_vp]),
     "lcbi_bias_grad": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int, c_vp]),
+    "lcbi_set_window_kernel_mode": (ctypes.c_int, [ctypes.c_int]),
     "lcbi_set_reserved_sms": (ctypes.c_int, [ctypes.c_int]),
     "lcbi_get_reserved_sms": (ctypes.c_int, []),
     "lcbi_window_maps": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_i32p, c_i32p, c_vp]),

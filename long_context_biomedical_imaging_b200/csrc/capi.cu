@@ -46,7 +46,9 @@ static int current_device_slot() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   return dev;
 }
+static int g_window_kernel_mode = 0;
 namespace lcbi {
+int window_kernel_mode() { return __atomic_load_n(&g_window_kernel_mode, __ATOMIC_RELAXED); }
 int reserved_sms() { return __atomic_load_n(&g_reserved_sms[current_device_slot()], __ATOMIC_RELAXED); }
 
 bool first_launch_on_current_device(unsigned long long* seen_mask) {
@@ -90,6 +92,12 @@ int lcbi_set_reserved_sms(int n) {
 int lcbi_get_reserved_sms(void) { return lcbi::reserved_sms(); }
 
 const char* lcbi_last_error(void) { return g_err; }
+
+int lcbi_set_window_kernel_mode(int mode) {
+  if (mode < 0 || mode > 2) return fail(LCBI_ERR_BAD_ARG, "lcbi_set_window_kernel_mode: expected 0 (auto), 1 (tcgen05) or 2 (generic)");
+  __atomic_store_n(&g_window_kernel_mode, mode, __ATOMIC_RELAXED);
+  return LCBI_OK;
+}
 
 int lcbi_dense_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq,
                         int Nk, int head_dim, const int64_t* q_strides, const int64_t* k_strides,

@@ -29,6 +29,7 @@ namespace lcbi {
 int win_attn_fwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream);   // window_attn_small.cu
 int win_attn_bwd_small_launch(const WinParams& p, int head_dim, cudaStream_t stream);   // window_attn_small.cu
 bool win_attn_tc_applicable(const WinParams& p, int head_dim);                           // window_attn_tc.cu
+int window_kernel_mode();                                                                // capi.cu: 0 auto, 1 tcgen05, 2 generic
 int win_attn_fwd_tc_launch(const WinParams& p, int head_dim, cudaStream_t stream);       // window_attn_tc.cu
 int win_attn_bwd_tc_launch(const WinParams& p, int head_dim, cudaStream_t stream);       // window_attn_tc.cu
 
@@ -866,8 +867,18 @@ int win_attn_fwd_launch(const WinAttnArgs& a, cudaStream_t stream) {
   // CTA-per-(window, head) kernel below fills the machine better (measured).
   static const bool legacy_small_fwd = std::getenv("LCBI_WIN_LEGACY_FWD") != nullptr;
   if (p.g.n <= 64 && p.win_count >= 1024 && !legacy_small_fwd) return win_attn_fwd_small_launch(p, a.head_dim, stream);
-  // 3-D windows of 128..512 tokens (7^3, 8^3): tcgen05 / TMEM kernel fed by TMA box / gather4 loads (window_attn_tc.cu)
-  if (win_attn_tc_applicable(p, a.head_dim)) return win_attn_fwd_tc_launch(p, a.head_dim, stream);
+  // 3-D windows of 128..512 tokens (7^3, 8^3): tcgen05 / TMEM kernel fed by TMA box / gather4 loads (window_attn_tc.cu).
+  // Measured on B200 (profiles/r02_swin_tc_vs_generic.log): its persistent CTAs are on par with the generic kernel when
+  // there are many (window, head) items per SM (cfg4 stage 1: 256 vs 251 us) and lose when a CTA gets one or two items
+  // (stages 2-4) or with head_dim 32, so that is where the line is drawn; lcbi_set_window_kernel_mode overrides it.
+  if (win_attn_tc_applicable(p, a.head_dim)) {
+    const int mode = window_kernel_mode();
+    const bool use_tc = mode == 1 || (mode == 0 && a.head_dim == 16 && p.win_count * p.H >= 1536);
+    if (use_tc) {
+      rc = win_attn_fwd_tc_launch(p, a.head_dim, stream);
+      if (rc != LCBI_ERR_UNSUPPORTED) return rc;
+    }
+  }
   const size_t smem = fwd_smem_bytes(p.g, a.head_dim);
   dim3 grid(p.win_count, p.H);
   if (a.head_dim == 16) {
@@ -909,10 +920,15 @@ int win_attn_bwd_launch(const WinAttnArgs& a, const void* o, cudaStream_t stream
   if (p.g.n <= 64 && !legacy_small_bwd) return win_attn_bwd_small_launch(p, D, stream);
   // 3-D windows of 128..512 tokens: ONE tcgen05 kernel produces dq, dk, dv, the pad-token bias gradient and d(table) with
   // a single recompute of S (window_attn_tc.cu); shapes whose operands do not fit its shared memory fall through
-  static const bool no_tc_bwd = std::getenv("LCBI_WIN_NO_TC_BWD") != nullptr;
-  if (!no_tc_bwd && win_attn_tc_applicable(p, D)) {
-    rc = win_attn_bwd_tc_launch(p, D, stream);
-    if (rc != LCBI_ERR_UNSUPPORTED) return rc;
+  // Measured (same log): faster than the two generic kernels for head_dim 16 up to ~1500 items (cfg4 stages 2-4: 385 vs
+  // 461, 224 vs 293, 173 vs 195 us), 10 % slower at stage 1 (3000 items) and slower for head_dim 32 (no room to prefetch).
+  if (win_attn_tc_applicable(p, D)) {
+    const int mode = window_kernel_mode();
+    const bool use_tc = mode == 1 || (mode == 0 && D == 16 && p.win_count * p.H < 1536);
+    if (use_tc) {
+      rc = win_attn_bwd_tc_launch(p, D, stream);
+      if (rc != LCBI_ERR_UNSUPPORTED) return rc;
+    }
   }
   // 2. dK, dV (+ pad-token bias gradient)
   {

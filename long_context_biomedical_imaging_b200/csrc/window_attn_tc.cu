@@ -1053,8 +1053,6 @@ uint32_t align_up_u32(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 // relative-position geometry is the window's own), with 7x7 or 8x8 planes, 2..8 planes (128 < n <= 512), and shifts that
 // are all zero or the reference's window // 2 (backbone_swin.py:675,687).
 bool win_attn_tc_applicable(const WinParams& p, int head_dim) {
-  static const bool disabled = std::getenv("LCBI_WIN_NO_TC") != nullptr;
-  if (disabled) return false;
   const WinGeom& g = p.g;
   if (head_dim != 16 && head_dim != 32) return false;
   if (g.grid[0] <= 1 || g.n <= 128 || g.n > 512) return false;

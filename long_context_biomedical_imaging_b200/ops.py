@@ -597,6 +597,13 @@ def window_attention(qkv, qkv_bias, table, grid, window, shift, num_heads, scale
     return out if out.dtype == qkv.dtype else out.to(qkv.dtype)
 
 
+def set_window_kernel_mode(mode):
+    """'auto' (default: tcgen05 kernels where measured at least as fast), 'tcgen05' or 'generic' for 3-D windows of
+    128..512 tokens (C ABI lcbi_set_window_kernel_mode); used by the parity tests to cover both kernel families."""
+    code = {"auto": 0, "tcgen05": 1, "generic": 2}[mode]
+    _lib.check(_lib.load().lcbi_set_window_kernel_mode(code), "lcbi_set_window_kernel_mode")
+
+
 def window_maps(grid, window, shift, device="cuda"):
     """(gather_map (nW,n) int32, region_ids (nW,n) int32, rel_pos_index (n,n) int32) computed by the CUDA code
     path's own closed forms — for bit-exactness tests against the reference's pad/roll/partition/compute_mask."""

@@ -137,8 +137,23 @@ def test_swin_encoder_drop_in_vs_golden(name):
     ((32, 32), (7, 7), (3, 3), 384, 12, 16),            # cfg2 stage 3
     ((128, 128), (7, 7), (3, 3), 96, 3, 16),            # cfg2 stage 1 at the bench batch
 ])
-def test_window_attention_op_vs_oracle_at_config_geometry(grid, window, shift, C, H, B):
-    """The raw fused op (no Linear layers) against the oracle's gather/attention/scatter on the GPU in fp32."""
+@pytest.mark.parametrize("mode", ["tcgen05", "generic"])
+def test_window_attention_op_vs_oracle_at_config_geometry(grid, window, shift, C, H, B, mode):
+    """The raw fused op (no Linear layers) against the oracle's gather/attention/scatter on the GPU in fp32, once with
+    the tcgen05 / TMA kernels forced wherever they apply (3-D windows of 128..512 tokens) and once with the generic
+    kernels only (the default picks per shape by measured speed)."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    if mode == "generic" and (len(grid) == 2 or B > 2):
+        pytest.skip("2-D windows have one kernel family; covered by the tcgen05-mode run")
+    ops.set_window_kernel_mode(mode)
+    try:
+        _window_attention_vs_oracle(grid, window, shift, C, H, B)
+    finally:
+        ops.set_window_kernel_mode("auto")
+
+
+def _window_attention_vs_oracle(grid, window, shift, C, H, B):
     from long_context_biomedical_imaging_b200 import ops
 
     torch.manual_seed(0)
