@@ -303,6 +303,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 #define LCBI_R4(a, i) "=r"(a[i]), "=r"(a[i + 1]), "=r"(a[i + 2]), "=r"(a[i + 3])
 #define LCBI_W4(a, i) "r"(a[i]), "r"(a[i + 1]), "r"(a[i + 2]), "r"(a[i + 3])
 
+__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : LCBI_R4(r, 0), LCBI_R4(r, 4)

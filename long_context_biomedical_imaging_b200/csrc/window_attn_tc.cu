@@ -484,6 +484,8 @@ win_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_dense, const __gri
 //   dP^T = V_kt dO_a^T - D          A = V tile                   B = dO plane                    per-query term (hi,mid,lo)
 //   compute warps 0-3 (thread = key row, all columns of the plane):
 //     P^T = exp2(S^T c + bias [+ mask]);  dS^T = P^T o dP^T;  P^T, dS^T -> bf16 in place in TMEM;  dS^T -> swizzled smem tile
+//   table warps 6-9 (thread = key row again, one warp per 32 keys, sharing an SM sub-partition with a compute warp):
+//     read their rows of the dS^T smem tile back and do
 //     d(bias table)[idx(i, j)] += dS^T into a per-warp fp32 table in shared memory, without atomics: KEYS are held in
 //     W-MAJOR order (row = c'*(WD*PH) + a'*PH + b'), so the 32 keys of a warp share one c' (two adjacent ones where a
 //     warp straddles a group). Two (key, query) pairs of a warp then hit the same table entry only if the queries' c
@@ -492,7 +494,7 @@ win_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_dense, const __gri
 //     loads, adds and stores of 3-4 entries are independent.
 //   dV_kt += P^T dO_a,  dK_kt += dS^T Q_a   (TS MMAs, B MN-major);  every second plane: dQ_pair += dS K_kt (A = the dS^T
 //   smem tile read MN-major, M = 128 queries = two planes).  dK/dV leave TMEM per key tile, dQ (all planes) per item.
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 320;          // warps 0-3 compute, 4 issuer, 5 gather, 6-9 d(bias table)
 constexpr int kAugBytes = kChunk * 16;       // [64 query rows x 8 bf16], un-swizzled core-matrix layout (row r at r*16)
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256;
 
@@ -513,6 +515,7 @@ struct TcBwdParams {
 struct BwdBars {
   uint64_t full[2], ready[2], free_[2];
   uint64_t sdp_full[2], pds_full[2], dq_done, dkv_full, dkv_drained, dq_full, dq_drained;
+  uint64_t ds_read[2];      // the table warps have read atom x of the dS^T tile
   uint32_t tmem_base;
   int buf_head[2];
 };
@@ -587,6 +590,8 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
       mbar_init(&bars.pds_full[b], 4);
       bars.buf_head[b] = -1;
     }
+    mbar_init(&bars.ds_read[0], 4);
+    mbar_init(&bars.ds_read[1], 4);
     mbar_init(&bars.dq_done, 1);
     mbar_init(&bars.dkv_full, 1);
     mbar_init(&bars.dkv_drained, 4);
@@ -803,15 +808,9 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
     const float cs = p.w.scale_log2;
     const float sc = p.w.scale_log2 / kLog2e;            // the softmax scale itself (q is scaled before q k^T)
-    float* const dtab = kStaticDtab ? s_dtab[kStaticDtab ? warp : 0] : reinterpret_cast<float*>(smem + p.off_dtab + warp * p.dtab_stride);
     int cur_head = -1;
-    auto flush_head = [&](int head) {       // accumulated d(bias table) and pad-token bias gradient -> global, then cleared
+    auto flush_head = [&](int head) {       // accumulated pad-token bias gradient -> global, then cleared
       if (head < 0) return;
-      for (int t = lane; t < g.tab_rows; t += 32) {
-        const float v = dtab[t];
-        if (v != 0.f) atomicAdd(p.w.dtable + static_cast<size_t>(t) * p.w.H + head, v);
-        dtab[t] = 0.f;
-      }
       named_bar_sync(1, 128);               // every warp's pad-gradient adds of the old head have landed
       if (tid < 3 * D) {
         const float v = s_dpad[tid];
@@ -832,6 +831,7 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
       }
     };
     int gs0 = 0, gt = 0, gp_seen = 0, it = 0;
+    int atom_writes[2] = {0, 0};
     for (int item = item_begin; item < item_end; ++item, ++it) {
       const int buf = p.nbuf == 2 ? (it & 1) : 0, use = p.nbuf == 2 ? (it >> 1) : it;
       const WinInfo wi = window_info(p.w, item);
@@ -860,14 +860,22 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
           const int gs = gs0 + a, b = gs & 1;
           mbar_wait(&bars.sdp_full[b], (gs >> 1) & 1);
           tc_fence_after();
-          uint32_t sv[64], dpv[64];
+          // only the plane's PLANE columns are loaded (49 = 32 + 16 + 1): registers are short with three warps on two
+          // of the SM sub-partitions
+          uint32_t sv[PLANE], dpv[PLANE];
           tmem_ld_x32(tmem + lane_sel + kTmemS + b * kChunk, sv);
-          tmem_ld_x32(tmem + lane_sel + kTmemS + b * kChunk + 32, sv + 32);
           tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kChunk, dpv);
-          tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kChunk + 32, dpv + 32);
+          if (PLANE == 64) {
+            tmem_ld_x32(tmem + lane_sel + kTmemS + b * kChunk + 32, sv + 32);
+            tmem_ld_x32(tmem + lane_sel + kTmemDP + b * kChunk + 32, dpv + 32);
+          } else {
+            tmem_ld_x16(tmem + lane_sel + kTmemS + b * kChunk + 32, sv + 32);
+            tmem_ld_x16(tmem + lane_sel + kTmemDP + b * kChunk + 32, dpv + 32);
+            tmem_ld_x1(tmem + lane_sel + kTmemS + b * kChunk + 48, sv + 48);
+            tmem_ld_x1(tmem + lane_sel + kTmemDP + b * kChunk + 48, dpv + 48);
+          }
           tmem_ld_wait();
           const float* trow = s_tab + t_base + a * ST0;
-          float* drow = dtab + t_base + a * ST0;
           float mv[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
           if (masked) {
             const bool da = wi.str[0] && (hi_a != (a >= g.win[0] - g.shift[0]));
@@ -879,7 +887,6 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
           }
           // P^T = exp2(s c + bias [+ mask]) (the per-query -lse2 arrived through the extra k-step), dS^T = P^T o dP^T
           // (a phase-structured variant with packed FFMA2 / FMUL2 was measured slower: 1552 vs 1459 us per cfg4 block)
-          float ds[PLANE];
           uint32_t pk[32], dsk[32];
 #pragma unroll
           for (int e = 0; e < kChunk; e += 2) {
@@ -890,7 +897,6 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
               if (masked) x += mv[qb >= PH - PH / 2][qc >= PW - PW / 2];
               p0 = fast_exp2(x);
               d0 = p0 * __uint_as_float(dpv[e]);
-              ds[e] = d0;
             }
             if (e + 1 < PLANE) {
               const int qb = (e + 1) / PW, qc = (e + 1) % PW;
@@ -898,34 +904,18 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
               if (masked) x += mv[qb >= PH - PH / 2][qc >= PW - PW / 2];
               p1 = fast_exp2(x);
               d1 = p1 * __uint_as_float(dpv[e + 1]);
-              ds[e + 1] = d1;
             }
             pk[e / 2] = pack_bf16x2(p0, p1);
             dsk[e / 2] = pack_bf16x2(d0, d1);
           }
           tmem_st_x32(tmem + lane_sel + kTmemS + b * kChunk, pk);
           tmem_st_x32(tmem + lane_sel + kTmemDP + b * kChunk, dsk);
-          // d(bias table) += dS^T in hazard-free rounds (see the header): plane row qb, even query columns then odd ones
-          // (with 8-wide planes a warp never straddles two key groups, so a whole row is one round)
-          // rows past the window (tile padding) load and add like the others but do not store
-#pragma unroll
-          for (int qb = 0; qb < PH; ++qb) {
-#pragma unroll
-            for (int par = 0; par < ((PW & 1) ? 2 : 1); ++par) {
-              float acc[PW];
-#pragma unroll
-              for (int qc = par; qc < PW; qc += ((PW & 1) ? 2 : 1)) acc[qc] = drow[qb * ST1 + qc];
-#pragma unroll
-              for (int qc = par; qc < PW; qc += ((PW & 1) ? 2 : 1)) acc[qc] += ds[qb * PW + qc];
-#pragma unroll
-              for (int qc = par; qc < PW; qc += ((PW & 1) ? 2 : 1))
-                if (row_valid) drow[qb * ST1 + qc] = acc[qc];
-              __syncwarp();
-            }
-          }
           // dS^T -> the smem tile dQ reads (atom = plane parity). The tile is single-buffered: the dQ MMA of the previous
           // plane pair must have retired before the first atom is overwritten (it was issued a whole step ago).
           if ((a & 1) == 0 && gp_seen > 0) mbar_wait(&bars.dq_done, (gp_seen - 1) & 1);
+          // ... and the table warps must have read this atom's previous contents
+          if (atom_writes[a & 1] > 0) mbar_wait(&bars.ds_read[a & 1], (atom_writes[a & 1] - 1) & 1);
+          ++atom_writes[a & 1];
           uint8_t* atom = s_ds + (a & 1) * kAtomBytes;
 #pragma unroll
           for (int c16 = 0; c16 < 8; ++c16)
@@ -1008,6 +998,74 @@ win_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_colgrp, const __gr
       }
     }
     flush_head(cur_head);
+  }
+
+  if (warp >= 6) {
+    // ------------------------------------------------------------------ d(relative_position_bias_table) (warps 6-9)
+    const int qw = warp - 6;                               // which 32 keys of the tile
+    float* const dtab = kStaticDtab ? s_dtab[kStaticDtab ? qw : 0] : reinterpret_cast<float*>(smem + p.off_dtab + qw * p.dtab_stride);
+    int cur_head = -1;
+    auto flush_dtab = [&](int head) {       // this warp's accumulated d(bias table) -> global, then cleared
+      if (head < 0) return;
+      for (int t = lane; t < g.tab_rows; t += 32) {
+        const float v = dtab[t];
+        if (v != 0.f) atomicAdd(p.w.dtable + static_cast<size_t>(t) * p.w.H + head, v);
+        dtab[t] = 0.f;
+      }
+      __syncwarp();
+    };
+    int gs0 = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const WinInfo wi = window_info(p.w, item);
+      if (wi.h != cur_head) {
+        flush_dtab(cur_head);
+        cur_head = wi.h;
+      }
+      for (int kt = 0; kt < p.kt; ++kt, gs0 += p.npl) {
+        const int trow_i = qw * 32 + lane;                 // row inside the 128-key tile
+        const int row = kt * kTileM + trow_i;              // key row, W-major: c' * gsp + a' * PH + b'
+        const bool row_valid = row < p.n_krows && (row % p.gsp) < p.gs;
+        const int krow = row_valid ? row : 0;
+        const int cj = krow / p.gsp, rem = krow - cj * p.gsp;
+        const int aj = rem / PH, bj = rem - aj * PH;
+        const int t_base = (g.win[0] - 1 - aj) * ST0 + (PH - 1 - bj) * ST1 + (PW - 1 - cj);
+        for (int a = 0; a < p.npl; ++a) {
+          const int gs = gs0 + a, b = gs & 1;
+          mbar_wait(&bars.pds_full[b], (gs >> 1) & 1);     // the compute warps have written this plane's dS^T atom
+          const uint8_t* atom = s_ds + (a & 1) * kAtomBytes;
+          uint32_t raw[28];                                 // 56 bf16 >= PLANE query columns of this key row
+#pragma unroll
+          for (int c16 = 0; c16 < 7; ++c16) {
+            const uint4 x = *reinterpret_cast<const uint4*>(atom + sw128_offset(trow_i, c16));
+            raw[c16 * 4] = x.x; raw[c16 * 4 + 1] = x.y; raw[c16 * 4 + 2] = x.z; raw[c16 * 4 + 3] = x.w;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.ds_read[a & 1]);
+          float* drow = dtab + t_base + a * ST0;
+          auto dsv = [&](int e) {                            // element e of the row (bf16 -> fp32)
+            return (e & 1) ? __uint_as_float(raw[e >> 1] & 0xFFFF0000u) : __uint_as_float(raw[e >> 1] << 16);
+          };
+          // hazard-free rounds (see the header): plane row qb, even query columns then odd ones (with 8-wide planes a
+          // warp never straddles two key groups, so a whole row is one round); rows past the window do not store
+#pragma unroll
+          for (int qb = 0; qb < PH; ++qb) {
+#pragma unroll
+            for (int par = 0; par < ((PW & 1) ? 2 : 1); ++par) {
+              float acc[PW];
+#pragma unroll
+              for (int qc = par; qc < PW; qc += ((PW & 1) ? 2 : 1)) acc[qc] = drow[qb * ST1 + qc];
+#pragma unroll
+              for (int qc = par; qc < PW; qc += ((PW & 1) ? 2 : 1)) acc[qc] += dsv(qb * PW + qc);
+#pragma unroll
+              for (int qc = par; qc < PW; qc += ((PW & 1) ? 2 : 1))
+                if (row_valid) drow[qb * ST1 + qc] = acc[qc];
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+    flush_dtab(cur_head);
   }
 
   tc_fence_before();
