@@ -112,6 +112,22 @@ int lcbi_patch_embed_fwd(const void* img, int img_is_bf16, const float* w, const
 int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
                          float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
                          const int* patch, const int* grid, int N, void* stream);
+/* The same forward with a caller-owned workspace of lcbi_patch_embed_workspace_bytes(B, Cin, patch, grid, N) bytes
+ * (128-byte aligned). With it, reduction lengths K = Cin*prod(patch) that are multiples of 64 (cfg1 K = 256, cfg3
+ * K = 512; fp32 image, patch width a multiple of 8) run on tcgen05 / TMEM: a pre-pass writes the patches and the
+ * weights as bf16 (hi, lo) pairs into the workspace, and a TMA-fed GEMM with three tensor-core products per k-step
+ * keeps fp32 accuracy (max-rel ~2e-5). Other shapes, or workspace == NULL, take the kernels of lcbi_patch_embed_fwd. */
+size_t lcbi_patch_embed_workspace_bytes(int B, int Cin, const int* patch, const int* grid, int N);
+int lcbi_patch_embed_fwd_ws(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
+                            void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
+                            const int* grid, int N, void* workspace, size_t workspace_bytes, void* stream);
+/* The backward with the same workspace: for the shapes above and fp32 dout, dw = dout^T * patches runs on tcgen05 with
+ * both operands split into bf16 (hi, lo) pairs in the workspace (the M patches are the contraction; partial tiles of
+ * the M-split are added into dw), and dbias rides on the split of dout. dpos / dimg as in lcbi_patch_embed_bwd. */
+int lcbi_patch_embed_bwd_ws(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
+                            float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
+                            const int* patch, const int* grid, int N, void* workspace, size_t workspace_bytes,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Swin (shifted-)window attention. Replaces, as ONE gather -> attention -> scatter kernel, the body of

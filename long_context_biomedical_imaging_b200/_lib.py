@@ -36,8 +36,15 @@ SIGNATURES = {
                                        ctypes.c_int, ctypes.c_int, c_vp]),
     "lcbi_patch_embed_fwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
+    "lcbi_patch_embed_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, ctypes.c_int]),
+    "lcbi_patch_embed_fwd_ws": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp, ctypes.c_size_t,
+                                               c_vp]),
     "lcbi_patch_embed_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
                                             ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp]),
+    "lcbi_patch_embed_bwd_ws": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
+                                               ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, c_vp,
+                                               ctypes.c_size_t, c_vp]),
     "lcbi_win_attn_fwd": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lcbi_win_attn_bwd": (ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,

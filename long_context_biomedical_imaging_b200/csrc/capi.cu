@@ -200,14 +200,46 @@ int lcbi_patch_embed_fwd(const void* img, int img_is_bf16, const float* w, const
   return rc;
 }
 
+size_t lcbi_patch_embed_workspace_bytes(int B, int Cin, const int* patch, const int* grid, int N) {
+  if (!patch || !grid || B <= 0 || Cin <= 0 || N <= 0) return 0;
+  return patch_embed_tc_workspace_bytes(static_cast<int64_t>(B) * grid[0] * grid[1] * grid[2], N,
+                                        Cin * patch[0] * patch[1] * patch[2]);
+}
+
+int lcbi_patch_embed_fwd_ws(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
+                            void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
+                            const int* grid, int N, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!img || !w || !bias || !out || !img_dims || !patch || !grid)
+    return fail(LCBI_ERR_BAD_ARG, "lcbi_patch_embed_fwd_ws: null pointer argument");
+  if (B <= 0 || Cin <= 0 || N <= 0) return fail(LCBI_ERR_BAD_ARG, "lcbi_patch_embed_fwd_ws: non-positive size");
+  if (workspace != nullptr && patch_embed_tc_applicable(img_is_bf16, Cin, img_dims, patch, grid, N)) {
+    int rc = patch_embed_tc_fwd_launch(img, w, bias, pos, out, out_is_bf16, B, Cin, img_dims, patch, grid, N, workspace,
+                                       workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (rc == LCBI_ERR_WORKSPACE) return fail(rc, "lcbi_patch_embed_fwd_ws: workspace too small or misaligned");
+    if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_patch_embed_fwd_ws: pointers must be 16-byte aligned");
+    if (rc == LCBI_ERR_TENSOR_MAP) return fail(rc, "lcbi_patch_embed_fwd_ws: TMA tensor map encode failed");
+    return rc;
+  }
+  return lcbi_patch_embed_fwd(img, img_is_bf16, w, bias, pos, out, out_is_bf16, B, Cin, img_dims, patch, grid, N, stream);
+}
+
 int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
                          float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
                          const int* patch, const int* grid, int N, void* stream) {
+  return lcbi_patch_embed_bwd_ws(img, img_is_bf16, w, dout, dout_is_bf16, dw, dbias, dpos, dimg, B, Cin, img_dims, patch, grid,
+                                 N, nullptr, 0, stream);
+}
+
+int lcbi_patch_embed_bwd_ws(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
+                            float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
+                            const int* patch, const int* grid, int N, void* workspace, size_t workspace_bytes, void* stream) {
   if (!img || !w || !dout || !dw || !img_dims || !patch || !grid)
     return fail(LCBI_ERR_BAD_ARG, "lcbi_patch_embed_bwd: null pointer argument");
   int rc = patch_embed_bwd_launch(img, img_is_bf16, w, dout, dout_is_bf16, dw, dbias, dpos, dimg, B, Cin, img_dims,
-                                  patch, grid, N, static_cast<cudaStream_t>(stream));
-  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_patch_embed_bwd: non-positive size");
+                                  patch, grid, N, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_patch_embed_bwd: non-positive size or misaligned pointer");
+  if (rc == LCBI_ERR_WORKSPACE) return fail(rc, "lcbi_patch_embed_bwd_ws: workspace too small or misaligned");
+  if (rc == LCBI_ERR_TENSOR_MAP) return fail(rc, "lcbi_patch_embed_bwd_ws: TMA tensor map encode failed");
   return rc;
 }
 

@@ -57,15 +57,27 @@ int current_device_sm_count();
 int patch_embed_fwd_launch(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
                            void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
                            const int* grid, int N, cudaStream_t stream);
+// workspace (optional): with it, shapes patch_embed_tc_applicable accepts take the tcgen05 weight-gradient path
 int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
                            float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
-                           const int* patch, const int* grid, int N, cudaStream_t stream);
+                           const int* patch, const int* grid, int N, cudaStream_t stream, void* workspace = nullptr,
+                           size_t workspace_bytes = 0);
 
 // tensor-core variants for K >= 64 at fp32 accuracy (patch_embed_mma.cu); `applicable` is a host-side shape test
 bool patch_embed_mma_applicable(int Cin, const int* img_dims, const int* patch, const int* grid, int N);
 int patch_embed_fwd_mma_launch(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
                                void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,
                                const int* grid, int N, cudaStream_t stream);
+
+// tcgen05 / TMEM / TMA implicit GEMM for K % 64 == 0, fp32 image (patch_embed_tc.cu); needs a workspace for the split operands
+bool patch_embed_tc_applicable(int img_is_bf16, int Cin, const int* img_dims, const int* patch, const int* grid, int N);
+size_t patch_embed_tc_workspace_bytes(int64_t M, int N, int K);
+int patch_embed_tc_fwd_launch(const void* img, const float* w, const float* bias, const float* pos, void* out, int out_is_bf16,
+                              int B, int Cin, const int* img_dims, const int* patch, const int* grid, int N, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream);
+int patch_embed_tc_bwd_w_launch(const void* img, const float* dout, float* dw, float* dbias, int B, int Cin, const int* img_dims,
+                                const int* patch, const int* grid, int N, void* workspace, size_t workspace_bytes,
+                                cudaStream_t stream);
 
 int patch_embed_bwd_w_mma_launch(const void* img, int img_is_bf16, const void* dout, int dout_is_bf16, float* dw,
                                  float* dbias, int B, int Cin, const int* img_dims, const int* patch, const int* grid,

@@ -383,7 +383,8 @@ int patch_embed_fwd_launch(const void* img, int img_is_bf16, const float* w, con
 
 int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, const void* dout, int dout_is_bf16,
                            float* dw, float* dbias, float* dpos, float* dimg, int B, int Cin, const int* img_dims,
-                           const int* patch, const int* grid, int N, cudaStream_t stream) {
+                           const int* patch, const int* grid, int N, cudaStream_t stream, void* workspace,
+                           size_t workspace_bytes) {
   PEGeom g;
   int rc = fill_geom(g, img_dims, patch, grid, B, Cin, N);
   if (rc) return rc;
@@ -421,6 +422,10 @@ int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, con
       if (dout_is_bf16) LCBI_PE_BSK(float, __nv_bfloat16); else LCBI_PE_BSK(float, float);
     }
 #undef LCBI_PE_BSK
+  } else if (workspace != nullptr && !dout_is_bf16 && patch_embed_tc_applicable(img_is_bf16, Cin, img_dims, patch, grid, N)) {
+    rc = patch_embed_tc_bwd_w_launch(img, static_cast<const float*>(dout), dw, dbias, B, Cin, img_dims, patch, grid, N, workspace,
+                                     workspace_bytes, stream);
+    if (rc) return rc;
   } else if (patch_embed_mma_applicable(Cin, img_dims, patch, grid, N)) {
     rc = patch_embed_bwd_w_mma_launch(img, img_is_bf16, dout, dout_is_bf16, dw, dbias, B, Cin, img_dims, patch, grid, N,
                                       stream);

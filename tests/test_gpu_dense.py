@@ -140,6 +140,9 @@ def test_patch_embed_vs_golden():
     (2, 1, (1, 48, 80), (1, 16, 16), 192),      # cfg1-like, K = 256, M = 30 (ragged tile)
     (3, 1, (16, 24, 40), (8, 8, 8), 200),       # cfg3-like, K = 512, N not a multiple of 128
     (2, 3, (1, 20, 24), (1, 4, 8), 72),         # K = 96: three 32-chunks, partial 128-wide k tile in the backward
+    (2, 1, (1, 224, 224), (1, 16, 16), 192),    # cfg1 in full: M = 392 (3 tiles + tail), N = 192 (1.5 feature tiles)
+    (2, 1, (32, 48, 96), (8, 8, 8), 768),       # cfg3 geometry per image row, M = 576, all 6 feature tiles, 4 dW k tiles
+    (1, 2, (1, 40, 64), (1, 8, 8), 136),        # K = 128 over two channels, N % 8 == 0 but not % 16
 ])
 def test_patch_embed_large_k_tensor_core_path_fp32_accuracy(shape):
     """The K >= 64 path multiplies hi/lo bf16 splits on the tensor cores; it must still meet the fp32 tolerance

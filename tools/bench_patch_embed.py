@@ -30,7 +30,11 @@ def timeit(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+
 for name, B, Cin, img, patch, N, vit in CASES:
+    if ONLY and not name.startswith(ONLY):
+        continue
     torch.manual_seed(0)
     x = torch.randn(B, Cin, *img, device="cuda")
     w = torch.randn(N, Cin, *patch, device="cuda", requires_grad=True)
