@@ -595,7 +595,17 @@ win_attn_bwd_small_kernel(const WinParams p) {
     }
   }
 
-  // ---- once per CTA: bias-table gradient and the pad-token share of d(qkv.bias)
+  // ---- once per CTA: bias-table gradient and the pad-token share of d(qkv.bias).
+  // Every CTA of a head adds into the same (2w-1)^2 table entries: going to global memory per (i, j) pair (2401 adds
+  // per CTA onto 169 addresses at 7x7) made the L2 serialise ~4000 same-address atomics per entry - a quarter of the
+  // kernel's stall samples at cfg2. The pairs are folded in shared memory first (the bias table and the P tile are dead
+  // by now), so that a CTA issues one global add per table entry and per pad-bias column.
+  __syncthreads();                                   // all warps are past their last read of tab / sP
+  float* s_dt = tab;                                 // [tab_rows]
+  float* s_dpad = reinterpret_cast<float*>(sP);      // [2 * D]
+  for (int t = tid; t < g.tab_rows; t += 128) s_dt[t] = 0.f;
+  if (tid < 2 * D) s_dpad[tid] = 0.f;
+  __syncthreads();
   if (p.dtable != nullptr && tile_live) {
     const int i0 = row0 + gq, i1 = i0 + 8;
     const int rt0 = s_rt[i0 < 64 ? i0 : 63], rt1 = s_rt[i1 < 64 ? i1 : 63];
@@ -606,12 +616,13 @@ win_attn_bwd_small_kernel(const WinParams p) {
         const int j = t8 * 8 + qq * 2 + e;
         if (j >= n) continue;
         const int ct = s_ct[j];
-        if (i0 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt0 - ct) * p.H + h, dbias[t8][e]);
-        if (i1 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt1 - ct) * p.H + h, dbias[t8][2 + e]);
+        if (i0 < n) atomicAdd(s_dt + (rt0 - ct), dbias[t8][e]);
+        if (i1 < n) atomicAdd(s_dt + (rt1 - ct), dbias[t8][2 + e]);
       }
     }
   }
-  if (p.dbias_pad != nullptr && g.n * g.nW != g.T) {
+  const bool has_pad_bias = p.dbias_pad != nullptr && g.n * g.nW != g.T;
+  if (has_pad_bias) {
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd) {
 #pragma unroll
@@ -623,12 +634,22 @@ win_attn_bwd_small_kernel(const WinParams p) {
           c += __shfl_xor_sync(0xffffffffu, c, off);
         }
         if (gq == 0) {
-          const int col = h * D + nd * 8 + qq * 2 + e;
-          if (a != 0.f) atomicAdd(p.dbias_pad + p.C + col, a);
-          if (c != 0.f) atomicAdd(p.dbias_pad + 2 * p.C + col, c);
+          const int col = nd * 8 + qq * 2 + e;
+          if (a != 0.f) atomicAdd(s_dpad + col, a);
+          if (c != 0.f) atomicAdd(s_dpad + D + col, c);
         }
       }
     }
+  }
+  __syncthreads();
+  if (p.dtable != nullptr)
+    for (int t = tid; t < g.tab_rows; t += 128) {
+      const float v = s_dt[t];
+      if (v != 0.f) atomicAdd(p.dtable + static_cast<int64_t>(t) * p.H + h, v);
+    }
+  if (has_pad_bias && tid < 2 * D) {
+    const float v = s_dpad[tid];
+    if (v != 0.f) atomicAdd(p.dbias_pad + (tid < D ? 1 : 2) * p.C + h * D + (tid < D ? tid : tid - D), v);
   }
 }
 
