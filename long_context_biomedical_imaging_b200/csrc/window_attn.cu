@@ -792,8 +792,13 @@ win_attn_bwd_dq_kernel(const WinParams p) {
     }
   }
 
-  // d(relative_position_bias_table)[idx(i,j), h] += dBias[i, j]   (window-independent index)
+  // d(relative_position_bias_table)[idx(i,j), h] += dBias[i, j]   (window-independent index).
+  // Folded in shared memory first (the bias table copy is dead by now): every CTA of a head targets the same few
+  // hundred cache lines, and per-(i, j) global adds serialise in the L2 (see window_attn_small.cu).
   if (p.dtable != nullptr) {
+    __syncthreads();                                 // all warps are past their last read of tab
+    for (int t = tid; t < g.tab_rows; t += nthreads) tab[t] = 0.f;
+    __syncthreads();
     int rt[2], ct_dummy;
     const int i0 = row_base + qt * 16 + gq, i1 = i0 + 8;
     relpos_terms(g, i0 < n ? i0 : 0, rt[0], ct_dummy);
@@ -806,9 +811,14 @@ win_attn_bwd_dq_kernel(const WinParams p) {
         if (j >= n) continue;
         int rtj, ctj;
         relpos_terms(g, j, rtj, ctj);
-        if (i0 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt[0] - ctj) * p.H + h, dbias[t16][e]);
-        if (i1 < n) atomicAdd(p.dtable + static_cast<int64_t>(rt[1] - ctj) * p.H + h, dbias[t16][2 + e]);
+        if (i0 < n) atomicAdd(tab + (rt[0] - ctj), dbias[t16][e]);
+        if (i1 < n) atomicAdd(tab + (rt[1] - ctj), dbias[t16][2 + e]);
       }
+    }
+    __syncthreads();
+    for (int t = tid; t < g.tab_rows; t += nthreads) {
+      const float v = tab[t];
+      if (v != 0.f) atomicAdd(p.dtable + static_cast<int64_t>(t) * p.H + h, v);
     }
   }
 }
