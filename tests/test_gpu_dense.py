@@ -175,6 +175,56 @@ def test_patch_embed_large_k_tensor_core_path_fp32_accuracy(shape):
     assert max_rel(x.grad.cpu(), gx.float().cpu()) < FP32_TOL
 
 
+@pytest.mark.parametrize("name,B,cin,dims,patch,hidden,vit", [
+    ("cfg2", 4, 1, (1, 512, 512), (1, 4, 4), 96, False),        # Swin-T 2D patch 4: K = 16, bf16 tokens
+    ("cfg4", 1, 1, (128, 128, 128), (2, 2, 2), 48, False),      # Swin 3D 'unetr' patch 2: K = 8
+    ("cfg5", 1, 1, (1, 1024, 1024), (1, 2, 2), 768, True),      # ViT-B 2D patch 2: K = 4, 262,144 tokens, fp32 + pos
+    ("pad", 2, 1, (1, 70, 90), (1, 4, 4), 32, False),           # trailing zero pad (PatchEmbed), ragged last chunk
+    ("cin3", 2, 2, (4, 12, 136), (2, 2, 2), 40, True),          # K = 16 over two channels, 68 patches per row (2 chunks)
+])
+def test_patch_embed_small_k_streaming_kernel_full_size(name, B, cin, dims, patch, hidden, vit):
+    """Full-size parity of the K in {4, 8, 16} streaming forward (and the small-K backward) against torch's fp32 strided
+    convolution: MONAI PatchEmbeddingBlock (ViT: + position embedding, fp32) and PatchEmbed (Swin: zero pad, bf16)."""
+    import torch.nn.functional as F
+    from long_context_biomedical_imaging_b200 import ops
+
+    def _mr(a, b):                                     # conftest.max_rel on the device (the cfg5 tensors hold 2e8 values)
+        return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+    torch.manual_seed(11)
+    x = torch.randn(B, cin, *dims, device="cuda")
+    w = (torch.randn(hidden, cin, *patch, device="cuda") * 0.2).requires_grad_(True)
+    b = torch.randn(hidden, device="cuda", requires_grad=True)
+    grid = [-(-s // p) for s, p in zip(dims, patch)]
+    n_tok = grid[0] * grid[1] * grid[2]
+    pos = torch.randn(1, n_tok, hidden, device="cuda", requires_grad=True) if vit else None
+    out_dtype = torch.float32 if vit else torch.bfloat16
+    y = ops.patch_embed(x, w, b, pos, grid, out_dtype)
+    pads = []
+    for s_, p_ in zip(reversed(dims), reversed(patch)):
+        pads += [0, (p_ - s_ % p_) % p_]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv3d(F.pad(x, pads), w, b, stride=patch).flatten(2).transpose(1, 2)
+        if pos is not None:
+            ref = ref + pos
+        dout = torch.randn(ref.shape, device="cuda", dtype=out_dtype)
+        grads = torch.autograd.grad(ref, (w, b) + ((pos,) if vit else ()), dout.float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert y.shape == ref.shape and y.dtype == out_dtype
+    if vit:
+        assert _mr(y.detach(), ref.detach()) < FP32_TOL
+    else:
+        assert _mr(y.detach().float(), ref.detach().to(torch.bfloat16).float()) < BF16_TOL
+    y.backward(dout)
+    assert _mr(w.grad, grads[0]) < 2e-4          # fp32 sums over up to 2.6e5 patches in a different order
+    assert _mr(b.grad, grads[1]) < 2e-4
+    if vit:
+        assert _mr(pos.grad, grads[2]) < FP32_TOL
+
+
 def _vit_cfg(hidden, mlp, layers, heads, patch, t, h, w, task="seg"):
     return types.SimpleNamespace(ViT=types.SimpleNamespace(size="custom", hidden_size=hidden, mlp_dim=mlp, num_layers=layers,
                                                            num_heads=heads, patch_size=list(patch), use_hyena=False,
