@@ -116,7 +116,8 @@ int lcbi_patch_embed_bwd(const void* img, int img_is_bf16, const float* w, const
  * (128-byte aligned). With it, reduction lengths K = Cin*prod(patch) that are multiples of 64 (cfg1 K = 256, cfg3
  * K = 512; fp32 image, patch width a multiple of 8) run on tcgen05 / TMEM: a pre-pass writes the patches and the
  * weights as bf16 (hi, lo) pairs into the workspace, and a TMA-fed GEMM with three tensor-core products per k-step
- * keeps fp32 accuracy (max-rel ~2e-5). Other shapes, or workspace == NULL, take the kernels of lcbi_patch_embed_fwd. */
+ * keeps fp32 accuracy (max-rel ~2e-5). Other shapes, or workspace == NULL, take the kernels of lcbi_patch_embed_fwd;
+ * lcbi_patch_embed_workspace_bytes returns 0 when no shape with this K uses a workspace. */
 size_t lcbi_patch_embed_workspace_bytes(int B, int Cin, const int* patch, const int* grid, int N);
 int lcbi_patch_embed_fwd_ws(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,
                             void* out, int out_is_bf16, int B, int Cin, const int* img_dims, const int* patch,

@@ -202,8 +202,9 @@ int lcbi_patch_embed_fwd(const void* img, int img_is_bf16, const float* w, const
 
 size_t lcbi_patch_embed_workspace_bytes(int B, int Cin, const int* patch, const int* grid, int N) {
   if (!patch || !grid || B <= 0 || Cin <= 0 || N <= 0) return 0;
-  return patch_embed_tc_workspace_bytes(static_cast<int64_t>(B) * grid[0] * grid[1] * grid[2], N,
-                                        Cin * patch[0] * patch[1] * patch[2]);
+  const int K = Cin * patch[0] * patch[1] * patch[2];
+  if (K < 64 || K % 64 != 0) return 0;          // no shape with this K takes the workspace path
+  return patch_embed_tc_workspace_bytes(static_cast<int64_t>(B) * grid[0] * grid[1] * grid[2], N, K);
 }
 
 int lcbi_patch_embed_fwd_ws(const void* img, int img_is_bf16, const float* w, const float* bias, const float* pos,

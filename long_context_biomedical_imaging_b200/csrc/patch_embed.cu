@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "lcbi_kernels.h"
+#include "window_common.cuh"      // FastDiv
 
 namespace lcbi {
 
@@ -27,6 +28,7 @@ struct PEGeom {
   int Gd, Gh, Gw;           // patch grid
   int N, K;                 // hidden, Cin*Pd*Ph*Pw
   int64_t M;                // B*Gd*Gh*Gw
+  FastDiv d_Gw, d_Gh, d_Gd, d_Pw, d_Ph, d_Pd;   // multiply-high divisors of the (patch, k) -> pixel map
 };
 
 __device__ __forceinline__ float load_px(const float* p) { return *p; }
@@ -34,6 +36,20 @@ __device__ __forceinline__ float load_px(const __nv_bfloat16* p) { return __bflo
 
 // image offset of (patch m, reduction index k), or -1 when it falls into the zero padding
 __device__ __forceinline__ int64_t px_offset(const PEGeom& g, int64_t m, int k) {
+  if (g.M < (1ll << 31)) {
+    // the usual case: every quotient fits 31 bits, six multiply-high divisions instead of ~10 runtime divisions (which
+    // were a large share of the instructions of the K <= 16 kernels: 4..16 pixels per patch leave little else to do)
+    int q, gw, gh, gd, b, kw, kh, kd, c;
+    fdivmod(static_cast<int>(m), g.d_Gw, q, gw);
+    fdivmod(q, g.d_Gh, q, gh);
+    fdivmod(q, g.d_Gd, b, gd);
+    fdivmod(k, g.d_Pw, q, kw);
+    fdivmod(q, g.d_Ph, q, kh);
+    fdivmod(q, g.d_Pd, c, kd);
+    const int z = gd * g.Pd + kd, y = gh * g.Ph + kh, x = gw * g.Pw + kw;
+    if (z >= g.D || y >= g.H || x >= g.W) return -1;
+    return (((static_cast<int64_t>(b) * g.Cin + c) * g.D + z) * g.H + y) * g.W + x;
+  }
   const int gw = static_cast<int>(m % g.Gw);
   const int gh = static_cast<int>((m / g.Gw) % g.Gh);
   const int gd = static_cast<int>((m / (static_cast<int64_t>(g.Gw) * g.Gh)) % g.Gd);
@@ -510,6 +526,8 @@ int fill_geom(PEGeom& g, const int* img_dims, const int* patch, const int* grid,
   g.N = N;
   g.K = Cin * patch[0] * patch[1] * patch[2];
   g.M = static_cast<int64_t>(B) * grid[0] * grid[1] * grid[2];
+  g.d_Gw = make_fastdiv(g.Gw); g.d_Gh = make_fastdiv(g.Gh); g.d_Gd = make_fastdiv(g.Gd);
+  g.d_Pw = make_fastdiv(g.Pw); g.d_Ph = make_fastdiv(g.Ph); g.d_Pd = make_fastdiv(g.Pd);
   return LCBI_OK;
 }
 

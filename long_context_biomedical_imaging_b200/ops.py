@@ -468,12 +468,12 @@ class _PatchEmbed(torch.autograd.Function):
         out = torch.empty((B, Np, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=img.device)
         lib = _lib.load()
         ws_bytes = lib.lcbi_patch_embed_workspace_bytes(B, Cin, _lib.int3(patch), _lib.int3(grid3), N)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=img_c.device)     # split operands of the tcgen05 path
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=img_c.device) if ws_bytes else None   # tcgen05 path
         with _on(img_c.device):
             rc = lib.lcbi_patch_embed_fwd_ws(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(b),
                                              _p(p) if p is not None else None, _p(out), int(out_bf16), B, Cin,
-                                             _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _p(ws), ws_bytes,
-                                             _stream(img_c.device))
+                                             _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N,
+                                             _p(ws) if ws is not None else None, ws_bytes, _stream(img_c.device))
         _lib.check(rc, "lcbi_patch_embed_fwd_ws")
         ctx.save_for_backward(img_c, w)
         ctx.geom = (img_dims, patch, grid3, B, Cin, N)
@@ -497,13 +497,13 @@ class _PatchEmbed(torch.autograd.Function):
         dimg = torch.empty(img_c.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
         lib = _lib.load()
         ws_bytes = lib.lcbi_patch_embed_workspace_bytes(B, Cin, _lib.int3(patch), _lib.int3(grid3), N)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)       # split operands of the tcgen05 dW path
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None     # tcgen05 dW path
         with _on(dev):
             rc = lib.lcbi_patch_embed_bwd_ws(_p(img_c), int(img_c.dtype == torch.bfloat16), _p(w), _p(dout),
                                              int(dout.dtype == torch.bfloat16), _p(dw), _p(db),
                                              _p(dpos) if dpos is not None else None, _p(dimg) if dimg is not None else None,
-                                             B, Cin, _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N, _p(ws),
-                                             ws_bytes, _stream(dev))
+                                             B, Cin, _lib.int3(img_dims), _lib.int3(patch), _lib.int3(grid3), N,
+                                             _p(ws) if ws is not None else None, ws_bytes, _stream(dev))
         _lib.check(rc, "lcbi_patch_embed_bwd_ws")
         return (dimg.to(img_dtype).view(img_shape) if dimg is not None else None, dw.view(w_shape).to(w_dtype),
                 db.to(b_dtype), dpos.view(pos_meta[0]).to(pos_meta[1]) if dpos is not None else None, None, None)
