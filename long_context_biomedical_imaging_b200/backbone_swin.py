@@ -405,7 +405,7 @@ class SwinTransformer_with_alt_ops(nn.Module):
         hidden_states_out = [x]
         out_dtype = torch.bfloat16 if (torch.is_autocast_enabled("cuda") and
                                        torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float32
-        t = self.pos_drop(self.patch_embed(x, out_dtype))          # channel-last token grid
+        t = self.pos_drop(self.patch_embed.forward_tokens(x, out_dtype))     # channel-last token grid
         hidden_states_out.append(self._out(t, normalize))
         for stage in (self.layers1, self.layers2, self.layers3, self.layers4):
             t = stage[0].forward_tokens(t)

@@ -149,8 +149,9 @@ class PatchEmbeddingBlock(nn.Module):
 class PatchEmbed(nn.Module):
     """Swin patch embedding: trailing zero-pad to a patch multiple + strided-conv projection.
 
-    forward returns the CHANNEL-LAST token grid (B, *grid, C); the Swin encoder exposes channel-first views of
-    it exactly where the reference returns channel-first tensors."""
+    `forward` returns what MONAI's PatchEmbed returns at the reference's `self.patch_embed(x)` seam
+    (backbone_swin.py:885): the CHANNEL-FIRST grid (B, C, *grid) - as a permuted view of the channel-last tokens the
+    kernel writes, so nothing is copied. The encoder itself calls `forward_tokens` and stays channel-last."""
 
     def __init__(self, patch_size: Sequence[int] | int = 2, in_chans: int = 1, embed_dim: int = 48, norm_layer=None,
                  spatial_dims: int = 3) -> None:
@@ -164,7 +165,12 @@ class PatchEmbed(nn.Module):
         self.proj = _ConvParams(in_chans, embed_dim, self.patch_size)
         self.norm = None
 
-    def forward(self, x, out_dtype=torch.float32):
+    def forward_tokens(self, x, out_dtype=torch.float32):
+        """Channel-last token grid (B, *grid, C)."""
         grid = tuple(-(-s // p) for s, p in zip(x.shape[2:], self.patch_size))   # ceil: trailing zero pad
         tokens = ops.patch_embed(x, self.proj.weight, self.proj.bias, None, grid, out_dtype)
         return tokens.view(x.shape[0], *grid, self.embed_dim)
+
+    def forward(self, x, out_dtype=torch.float32):
+        t = self.forward_tokens(x, out_dtype)
+        return t.permute(0, t.dim() - 1, *range(1, t.dim() - 1))

@@ -108,6 +108,17 @@ def test_swin_encoder_drop_in_vs_golden(name):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         outs = model(x)
     assert len(outs) == int(g[f"{name}/n_out"]) == 6
+    # the reference's `self.patch_embed(x)` seam (backbone_swin.py:885) returns MONAI's channel-first grid
+    import torch.nn.functional as F
+    xs = x.squeeze(2) if model.spatial_dims == 2 else x
+    pe = model.patch_embed(xs)
+    conv = F.conv2d if model.spatial_dims == 2 else F.conv3d
+    pads = []
+    for s_, p_ in zip(reversed(xs.shape[2:]), reversed(model.patch_embed.patch_size)):
+        pads += [0, (p_ - s_ % p_) % p_]
+    want_pe = conv(F.pad(xs, pads), model.patch_embed.proj.weight, model.patch_embed.proj.bias, stride=model.patch_embed.patch_size)
+    assert tuple(pe.shape) == tuple(want_pe.shape) and pe.shape[1] == kw["embed"]
+    assert max_rel(pe.detach().float().cpu(), want_pe.detach().float().cpu()) < 1e-3
     for i, o in enumerate(outs):
         want = g[f"{name}/out{i}"]
         assert tuple(o.shape) == want.shape, i
