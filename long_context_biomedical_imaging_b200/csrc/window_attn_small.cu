@@ -30,6 +30,12 @@ namespace {
 //     round trip per window);
 //   * the -100 shift-mask term is evaluated only for windows that straddle a region boundary.
 // =================================================================================================
+// Resident CTAs per SM the forward is compiled for. The kernel runs at ~0.1 IPC per warp (CTA barriers and dependent
+// ldmatrix -> mma -> shuffle chains per window), so more windows in flight is what helps: 4 CTAs (113 registers) 115.6 us,
+// 6 CTAs (80 registers, 32 bytes of spills) 97.0 us at cfg2 stage 1. The backward does not follow: capped to 128
+// registers for a fourth CTA it slows from 213.6 to 251 us (profiles/r02_small_window_tma_variant.log).
+constexpr int kFwdSmallCtas = 6;
+
 template <int D>
 struct SmallFwdSmem {
   static constexpr int kStride = Tile<D>::kStride;
@@ -38,7 +44,7 @@ struct SmallFwdSmem {
 };
 
 template <int D>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, kFwdSmallCtas)
 win_attn_fwd_small_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   using L = SmallFwdSmem<D>;
@@ -267,7 +273,7 @@ int launch_small(const WinParams& p, cudaStream_t stream) {
     }
   }
   const int units = p.win_count;
-  int grid_x = (2 * 148 * 4 + p.H - 1) / p.H;     // ~2 waves of persistent CTAs (4 per SM) per head slice
+  int grid_x = (2 * 148 * kFwdSmallCtas + p.H - 1) / p.H;     // ~2 waves of persistent CTAs per head slice
   if (grid_x > units) grid_x = units;
   if (grid_x < 1) grid_x = 1;
   win_attn_fwd_small_kernel<D><<<dim3(grid_x, p.H), 128, L::kTotal, stream>>>(p);
