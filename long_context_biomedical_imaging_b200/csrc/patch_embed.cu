@@ -516,6 +516,146 @@ void launch_fwd_stream(const void* img, int img_is_bf16, const float* w, const f
 #undef LCBI_PE_STREAM
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight / bias gradient for NARROW token rows (N < 256: the Swin configs, 48 / 96 features) and K in {4, 8, 16}: the
+// mirror of the streaming forward. patch_embed_bwd_smallk_kernel maps a warp to one 128-feature block of one row, so at
+// N = 48 twelve of its 32 lanes load 96 bytes per instruction and the kernel waits on memory (ncu: 63 % of the stall
+// samples on the dOut loads, 96 us for 25 MB at cfg4). Here threads are laid out (patch, feature group) in the memory
+// order of dOut - a warp's loads are one contiguous stream - the item's pixels are staged patch-major in shared memory
+// with the next item prefetched into registers, each thread keeps its 4 x K partial dW and 4 partial dbias in registers
+// over all items of the CTA, and the CTA folds them in shared memory before one global add per (feature, k).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KK, typename TIn, typename TG>
+__global__ void __launch_bounds__(256, KK == 16 ? 2 : 3)
+patch_embed_bwd_stream_kernel(const TIn* __restrict__ img, const TG* __restrict__ dout, float* __restrict__ dw,
+                              float* __restrict__ dbias, PEGeom g, int chunks_per_row, int n_items) {
+  constexpr int KS = KK + 4;
+  constexpr int kPre = kStreamRows * KK / 256;
+  __shared__ __align__(16) float s_a[kStreamRows * KS];
+  extern __shared__ float s_fold[];                           // [N][KK + 1]: the CTA's dW rows and dbias
+  const int tid = threadIdx.x;
+  const int tpp = g.N >> 2, ppp = 256 / tpp;
+  const int fg = tid % tpp, rs = tid / tpp;
+  for (int i = tid; i < g.N * (KK + 1); i += 256) s_fold[i] = 0.f;
+
+  const int run = kStreamRows * g.Pw;
+  int e_row[kPre], e_j[kPre], e_smem[kPre];                   // e_row = channel << 16 | kz << 8 | ky
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    const int e = tid + u * 256;
+    const int kr = e / run, j = e - kr * run;
+    const int ky = kr % g.Ph, kz = (kr / g.Ph) % g.Pd, cin = kr / (g.Ph * g.Pd);
+    const int r = j / g.Pw, px = j - r * g.Pw;
+    e_row[u] = (cin << 16) | (kz << 8) | ky;
+    e_j[u] = j;
+    e_smem[u] = r * KS + kr * g.Pw + px;
+  }
+  float pre[kPre];
+  auto fetch = [&](int item) {
+    const int prow = item / chunks_per_row, x0 = (item - prow * chunks_per_row) * kStreamRows;
+    const int gy = prow % g.Gh, t = prow / g.Gh;
+    const int gz = t % g.Gd, b = t / g.Gd;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int z = gz * g.Pd + ((e_row[u] >> 8) & 0xff), y = gy * g.Ph + (e_row[u] & 0xff), x = x0 * g.Pw + e_j[u];
+      float v = 0.f;
+      if (z < g.D && y < g.H && x < g.W)
+        v = load_px(img + (((static_cast<int64_t>(b) * g.Cin + (e_row[u] >> 16)) * g.D + z) * g.H + y) * g.W + x);
+      pre[u] = v;
+    }
+  };
+
+  float acc[4][KK], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[i][k] = 0.f;
+
+  int item = blockIdx.x;
+  if (item < n_items) fetch(item);
+  for (; item < n_items; item += gridDim.x) {
+    const int prow = item / chunks_per_row, x0 = (item - prow * chunks_per_row) * kStreamRows;
+    const int rv = min(kStreamRows, g.Gw - x0);
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) s_a[e_smem[u]] = pre[u];
+    __syncthreads();
+    if (item + static_cast<int>(gridDim.x) < n_items) fetch(item + gridDim.x);
+    if (rs < ppp) {
+      const TG* src = dout + (static_cast<int64_t>(prow) * g.Gw + x0) * g.N + fg * 4;
+#pragma unroll 2
+      for (int r = rs; r < rv; r += ppp) {
+        float gv[4];
+        if constexpr (sizeof(TG) == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r) * g.N));
+          gv[0] = t.x; gv[1] = t.y; gv[2] = t.z; gv[3] = t.w;
+        } else {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src + static_cast<int64_t>(r) * g.N));
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          gv[0] = lo.x; gv[1] = lo.y; gv[2] = hi.x; gv[3] = hi.y;
+        }
+        float a[KK];
+#pragma unroll
+        for (int k4 = 0; k4 < KK / 4; ++k4) {
+          const float4 t = *reinterpret_cast<const float4*>(s_a + r * KS + k4 * 4);
+          a[k4 * 4 + 0] = t.x; a[k4 * 4 + 1] = t.y; a[k4 * 4 + 2] = t.z; a[k4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          bsum[i] += gv[i];
+#pragma unroll
+          for (int k = 0; k < KK; ++k) acc[i][k] = fmaf(gv[i], a[k], acc[i][k]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // fold the patch lanes of the CTA (ppp threads per feature group) in shared memory, then one global add per value
+  if (rs < ppp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* row = s_fold + (fg * 4 + i) * (KK + 1);
+#pragma unroll
+      for (int k = 0; k < KK; ++k) atomicAdd(row + k, acc[i][k]);
+      atomicAdd(row + KK, bsum[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < g.N * (KK + 1); i += 256) {
+    const int col = i / (KK + 1), k = i - col * (KK + 1);
+    const float v = s_fold[i];
+    if (k == KK) {
+      if (dbias != nullptr) atomicAdd(dbias + col, v);
+    } else {
+      atomicAdd(dw + static_cast<int64_t>(col) * KK + k, v);
+    }
+  }
+}
+
+template <int KK>
+void launch_bwd_stream(const void* img, int img_is_bf16, const void* dout, int dout_is_bf16, float* dw, float* dbias,
+                       const PEGeom& g, cudaStream_t stream) {
+  const int chunks = (g.Gw + kStreamRows - 1) / kStreamRows;
+  const int n_items = static_cast<int>(static_cast<int64_t>(g.B) * g.Gd * g.Gh * chunks);
+  const int sms = current_device_sm_count();
+  const size_t fold_bytes = static_cast<size_t>(g.N) * (KK + 1) * sizeof(float);
+#define LCBI_PE_BSTREAM(TI, TG)                                                                                        \
+  do {                                                                                                                 \
+    int per_sm = 0;                                                                                                    \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, patch_embed_bwd_stream_kernel<KK, TI, TG>, 256, fold_bytes); \
+    const int want = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);                                                \
+    const unsigned blocks = static_cast<unsigned>(n_items < want ? n_items : want);                                    \
+    patch_embed_bwd_stream_kernel<KK, TI, TG><<<blocks, 256, fold_bytes, stream>>>(                                    \
+        static_cast<const TI*>(img), static_cast<const TG*>(dout), dw, dbias, g, chunks, n_items);                     \
+  } while (0)
+  if (img_is_bf16) {
+    if (dout_is_bf16) LCBI_PE_BSTREAM(__nv_bfloat16, __nv_bfloat16); else LCBI_PE_BSTREAM(__nv_bfloat16, float);
+  } else {
+    if (dout_is_bf16) LCBI_PE_BSTREAM(float, __nv_bfloat16); else LCBI_PE_BSTREAM(float, float);
+  }
+#undef LCBI_PE_BSTREAM
+}
+
 int fill_geom(PEGeom& g, const int* img_dims, const int* patch, const int* grid, int B, int Cin, int N) {
   if (B <= 0 || Cin <= 0 || N <= 0) return LCBI_ERR_BAD_ARG;
   for (int i = 0; i < 3; ++i)
@@ -582,7 +722,15 @@ int patch_embed_bwd_launch(const void* img, int img_is_bf16, const float* w, con
   }
   const int64_t np = static_cast<int64_t>(g.Gd) * g.Gh * g.Gw;
   bool dpos_done = false;
-  if (g.K <= kBwKMax && (N & 3) == 0) {
+  const bool narrow_stream = (g.K == 4 || g.K == 8 || g.K == 16) && g.K % g.Pw == 0 && (N & 3) == 0 && N < 256 &&
+                             g.Pd < 256 && g.Ph < 256 && Cin < 32768 &&
+                             static_cast<int64_t>(B) * g.Gd * g.Gh * ((g.Gw + kStreamRows - 1) / kStreamRows) < (1ll << 31) &&
+                             (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
+  if (narrow_stream) {
+    if (g.K == 4) launch_bwd_stream<4>(img, img_is_bf16, dout, dout_is_bf16, dw, dbias, g, stream);
+    else if (g.K == 8) launch_bwd_stream<8>(img, img_is_bf16, dout, dout_is_bf16, dw, dbias, g, stream);
+    else launch_bwd_stream<16>(img, img_is_bf16, dout, dout_is_bf16, dw, dbias, g, stream);
+  } else if (g.K <= kBwKMax && (N & 3) == 0) {
     // single pass over dOut; with B == 1 the position-embedding gradient is a cast/copy of dOut and rides along
     float* dpos_copy = (dpos != nullptr && B == 1) ? dpos : nullptr;
     dpos_done = dpos_copy != nullptr;
