@@ -41,6 +41,18 @@ def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
     assert rc == -1
     assert b"null pointer" in lib.lcbi_last_error()
     assert lib.lcbi_dense_attn_bwd_workspace_bytes(2, 3, 197, 64) >= 2 * 197 * 3 * 64 * 4 + 2 * 2 * 3 * 256 * 4
+    # patch embedding: a workspace only for reduction lengths the tcgen05 path takes (K % 64 == 0); host-side sizes
+    from long_context_biomedical_imaging_b200 import _lib
+
+    cfg3 = lib.lcbi_patch_embed_workspace_bytes(16, 1, _lib.int3((8, 8, 8)), _lib.int3((12, 12, 12)), 768)
+    m, k, n = 16 * 12 ** 3, 512, 768
+    assert cfg3 >= 2 * m * (k + n) * 2                       # split patches + split dOut, bf16 (hi, lo) pairs
+    assert lib.lcbi_patch_embed_workspace_bytes(1, 1, _lib.int3((1, 2, 2)), _lib.int3((1, 512, 512)), 768) == 0   # cfg5, K = 4
+    assert lib.lcbi_patch_embed_workspace_bytes(1, 1, None, None, 768) == 0
+    rc = lib.lcbi_patch_embed_fwd_ws(None, 0, None, None, None, None, 0, 1, 1, None, None, None, 8, None, 0, None)
+    assert rc == -1 and b"null pointer" in lib.lcbi_last_error()
+    rc = lib.lcbi_patch_embed_bwd_ws(None, 0, None, None, 0, None, None, None, None, 1, 1, None, None, None, 8, None, 0, None)
+    assert rc == -1 and b"null pointer" in lib.lcbi_last_error()
 
 
 def test_ops_refuse_cpu_tensors():

@@ -225,6 +225,37 @@ def test_patch_embed_small_k_streaming_kernel_full_size(name, B, cin, dims, patc
         assert _mr(pos.grad, grads[2]) < FP32_TOL
 
 
+def test_patch_embed_workspace_contract_through_the_c_abi():
+    """lcbi_patch_embed_fwd_ws: a short or misaligned workspace is refused with a message (no silent fallback onto a
+    different kernel), NULL selects the workspace-free kernels, and both give the same result as the full workspace."""
+    from long_context_biomedical_imaging_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(2)
+    B, dims, patch, N = 2, (1, 32, 48), (1, 8, 8), 64
+    grid = (1, 4, 6)
+    x = torch.randn(B, 1, *dims, device="cuda")
+    w = torch.randn(N, 64, device="cuda") * 0.1
+    b = torch.randn(N, device="cuda")
+    need = lib.lcbi_patch_embed_workspace_bytes(B, 1, _lib.int3(patch), _lib.int3(grid), N)
+    assert need > 0
+    ws = torch.empty(need + 256, dtype=torch.uint8, device="cuda")
+    outs = []
+    for ws_ptr, ws_bytes in ((ws.data_ptr(), need), (None, 0)):
+        out = torch.empty(B, 24, N, device="cuda")
+        rc = lib.lcbi_patch_embed_fwd_ws(x.data_ptr(), 0, w.data_ptr(), b.data_ptr(), None, out.data_ptr(), 0, B, 1,
+                                         _lib.int3(dims), _lib.int3(patch), _lib.int3(grid), N, ws_ptr, ws_bytes, None)
+        assert rc == 0, lib.lcbi_last_error()
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert max_rel(outs[0].cpu(), outs[1].cpu()) < FP32_TOL
+    out = torch.empty(B, 24, N, device="cuda")
+    for ws_ptr, ws_bytes in ((ws.data_ptr(), need - 1024), (ws.data_ptr() + 16, need)):
+        rc = lib.lcbi_patch_embed_fwd_ws(x.data_ptr(), 0, w.data_ptr(), b.data_ptr(), None, out.data_ptr(), 0, B, 1,
+                                         _lib.int3(dims), _lib.int3(patch), _lib.int3(grid), N, ws_ptr, ws_bytes, None)
+        assert rc != 0 and b"workspace" in lib.lcbi_last_error()
+
+
 def _vit_cfg(hidden, mlp, layers, heads, patch, t, h, w, task="seg"):
     return types.SimpleNamespace(ViT=types.SimpleNamespace(size="custom", hidden_size=hidden, mlp_dim=mlp, num_layers=layers,
                                                            num_heads=heads, patch_size=list(patch), use_hyena=False,
