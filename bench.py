@@ -388,6 +388,12 @@ def workload_cfg5(dist, rank, world, dev, steps=2, warmup=1):
     return out
 
 
+# dram__bytes_read + dram__bytes_write per step of the window-attention kernels (ncu --set full, one capture per kernel):
+# cfg2 (batch 16): forward 257.3 + 46.5 MB, backward 348.4 + 126.9 MB; cfg4: tcgen05 forward 89.6 + 10.8 MB, dK/dV
+# 107.1 + 44.0 MB, dQ 107.1 + 18.5 MB. Algorithmic bytes: 604 MB / 302 MB.
+SWIN_DRAM_BYTES_PER_STEP = {"cfg2": 779.1e6, "cfg4": 377.1e6}
+
+
 def workload_swin(name, dist, rank, world, dev, steps=30, warmup=5):
     """configs[1] / configs[3]: the window attention of one stage-1 Swin block (SW-MSA, shift = window // 2), fwd+bwd.
     cfg2 (Swin-T 2D, 512^2, patch 4 -> 128^2 tokens x 96 channels, 3 heads x 32, window 7, batch 16 per GPU) shards
@@ -461,7 +467,11 @@ def workload_swin(name, dist, rank, world, dev, steps=30, warmup=5):
            "roofline": {"bound": "hbm", "kernel": "window attention fwd + bwd launch group (through the autograd wrapper"
                                                   + (", incl. the collectives" if sharded else "") + ")",
                         "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                        "traffic": None, "algorithmic_bytes_per_step_per_gpu": alg_bytes},
+                        "traffic": None if sharded else SWIN_DRAM_BYTES_PER_STEP[name],
+                        "traffic_unit": "bytes per step on one GPU (dram read + write of the fwd + bwd window kernels, one ncu "
+                                        "--set full capture each: profiles/r02_ncu_cfg2_small_final_summary.csv, "
+                                        "r02_ncu_cfg4_final_summary.csv; the dK/dV kernel after the heads-fastest CTA order)",
+                        "algorithmic_bytes_per_step_per_gpu": alg_bytes},
            "gpu_launches_per_step_per_rank": 4}
     if n1_ms is not None:
         out["n1_ms_per_step_same_run"] = n1_ms
