@@ -215,6 +215,15 @@ int lcbi_add_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* dxsum, c
                             int delta_is_bf16, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
                             int64_t rows, int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row gather / scatter of the window-sharded Swin exchange (no reference counterpart: the reference has no window
+ * parallelism). Rows are row_bytes (a multiple of 16) contiguous bytes, ids are int64 on the device.
+ *   lcbi_gather_rows : dst[i, :] = src[ids[i], :]      i < n_rows   (pack the rank's window rows before the all-gather)
+ *   lcbi_scatter_rows: dst[ids[i], :] = src[i, :]      i < n_rows   (put every rank's rows back in token order)
+ * ---------------------------------------------------------------------------------------------- */
+int lcbi_gather_rows(const void* src, const int64_t* ids, void* dst, int64_t n_rows, int row_bytes, void* stream);
+int lcbi_scatter_rows(const void* src, const int64_t* ids, void* dst, int64_t n_rows, int row_bytes, void* stream);
+
 /* Bias gradient of the token-wise Linear layers that bracket the attention kernels (qkv with bias at
  * backbone_swin.py:309, out_proj / proj at backbone_vit.py:167,202 and backbone_swin.py:311,358, the MLP's
  * linear1 / linear2): dbias (C) fp32 = column sums of dy (rows, C) fp32 or bf16, C % 4 == 0, WRITTEN not accumulated.

@@ -65,6 +65,8 @@ SIGNATURES = {
     "lcbi_add_layer_norm_bwd": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                                ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64,
                                                ctypes.c_int, c_vp]),
+    "lcbi_gather_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int, c_vp]),
+    "lcbi_scatter_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int, c_vp]),
     "lcbi_bias_grad": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int, c_vp]),
     "lcbi_set_window_kernel_mode": (ctypes.c_int, [ctypes.c_int]),
     "lcbi_set_reserved_sms": (ctypes.c_int, [ctypes.c_int]),

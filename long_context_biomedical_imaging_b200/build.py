@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "liblcbi_b200.so")
 SOURCES = ["capi.cu", "dense_attn_fwd.cu", "dense_attn_bwd.cu", "window_attn.cu", "window_attn_small.cu", "window_attn_tc.cu", "patch_embed.cu", "patch_embed_mma.cu", "patch_embed_tc.cu",
-           "attn_merge.cu", "layer_norm.cu"]
+           "attn_merge.cu", "layer_norm.cu", "row_copy.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

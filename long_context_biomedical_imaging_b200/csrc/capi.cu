@@ -368,6 +368,20 @@ int lcbi_add_layer_norm_bwd(const void* dy, int dy_is_bf16, const void* dxsum, c
   return ln_status(rc, "lcbi_add_layer_norm_bwd");
 }
 
+int lcbi_gather_rows(const void* src, const int64_t* ids, void* dst, int64_t n_rows, int row_bytes, void* stream) {
+  if (n_rows > 0 && (!src || !ids || !dst)) return fail(LCBI_ERR_BAD_ARG, "lcbi_gather_rows: null pointer argument");
+  int rc = row_copy_launch(src, ids, dst, n_rows, row_bytes, 0, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_gather_rows: rows must be a positive multiple of 16 bytes, 16-byte aligned");
+  return rc;
+}
+
+int lcbi_scatter_rows(const void* src, const int64_t* ids, void* dst, int64_t n_rows, int row_bytes, void* stream) {
+  if (n_rows > 0 && (!src || !ids || !dst)) return fail(LCBI_ERR_BAD_ARG, "lcbi_scatter_rows: null pointer argument");
+  int rc = row_copy_launch(src, ids, dst, n_rows, row_bytes, 1, static_cast<cudaStream_t>(stream));
+  if (rc == LCBI_ERR_BAD_ARG) return fail(rc, "lcbi_scatter_rows: rows must be a positive multiple of 16 bytes, 16-byte aligned");
+  return rc;
+}
+
 int lcbi_bias_grad(const void* dy, int dy_is_bf16, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows,
                    int C, void* stream) {
   if (!dy || !dbias) return fail(LCBI_ERR_BAD_ARG, "lcbi_bias_grad: null pointer argument");

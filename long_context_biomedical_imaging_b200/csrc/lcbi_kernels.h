@@ -130,4 +130,9 @@ int add_layer_norm_bwd_launch(const void* dy, int y_is_bf16, const void* dres, c
 int bias_grad_launch(const void* dy, int dy_is_bf16, float* dbias, float* workspace, size_t workspace_bytes,
                      int64_t rows, int C, cudaStream_t stream);
 
+// window-sharded exchange: dst[i] = src[ids[i]] (scatter == 0) or dst[ids[i]] = src[i] (scatter != 0); rows of row_bytes
+// (a multiple of 16) contiguous bytes (row_copy.cu)
+int row_copy_launch(const void* src, const int64_t* ids, void* dst, int64_t n_rows, int row_bytes, int scatter,
+                    cudaStream_t stream);
+
 }  // namespace lcbi

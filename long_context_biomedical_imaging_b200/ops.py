@@ -517,6 +517,41 @@ def patch_embed(img, weight, bias, pos, grid, out_dtype=torch.float32):
 
 
 # --------------------------------------------------------------------------------------------------
+# Row gather / scatter (the exchange of the window-sharded Swin block, window_parallel.py)
+# --------------------------------------------------------------------------------------------------
+def _row_args(x2d, ids):
+    dev = _require_cuda(x2d, ids)
+    if x2d.dim() != 2 or not x2d.is_contiguous() or ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise ValueError("row copy: a contiguous (rows, F) tensor and contiguous int64 ids are required")
+    row_bytes = x2d.shape[1] * x2d.element_size()
+    if row_bytes % 16 != 0:
+        raise ValueError(f"row copy: rows must be a multiple of 16 bytes, got {row_bytes}")
+    return dev, row_bytes
+
+
+def gather_rows(src, ids):
+    """out[i] = src[ids[i]] (no autograd: the callers are autograd Functions)."""
+    dev, row_bytes = _row_args(src, ids)
+    out = torch.empty((ids.numel(), src.shape[1]), dtype=src.dtype, device=dev)
+    with _on(dev):
+        rc = _lib.load().lcbi_gather_rows(_p(src), _p(ids), _p(out), ids.numel(), row_bytes, _stream(dev))
+    _lib.check(rc, "lcbi_gather_rows")
+    return out
+
+
+def scatter_rows(src, ids, n_out_rows):
+    """out[ids[i]] = src[i] into a fresh (n_out_rows, F) tensor; rows no id points at are left uninitialised."""
+    dev, row_bytes = _row_args(src, ids)
+    if ids.numel() != src.shape[0]:
+        raise ValueError("scatter_rows: one id per source row")
+    out = torch.empty((n_out_rows, src.shape[1]), dtype=src.dtype, device=dev)
+    with _on(dev):
+        rc = _lib.load().lcbi_scatter_rows(_p(src), _p(ids), _p(out), ids.numel(), row_bytes, _stream(dev))
+    _lib.check(rc, "lcbi_scatter_rows")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # Swin window attention
 # --------------------------------------------------------------------------------------------------
 class _WindowAttention(torch.autograd.Function):

@@ -119,9 +119,16 @@ def _exchange_disjoint_rows(x2d, ids, n_rows, rank, group, world):
     """x2d: (n_rows, F) whose rows owned by this rank are valid. Returns the (n_rows, F) tensor in which every rank's
     owned rows are filled in: gather own rows -> all-gather -> scatter by token id. ids = (gather_ids, scatter_ids)."""
     gather_ids, scatter_ids = ids
-    mine = x2d.index_select(0, gather_ids[rank])
+    if x2d.is_cuda and (x2d.shape[1] * x2d.element_size()) % 16 == 0:
+        # streaming row copies (csrc/row_copy.cu): torch's index_select / index_copy_ ran at ~0.2 TB/s on these rows and
+        # were a quarter of the sharded step at cfg4 stage 1
+        from . import ops
+        mine = ops.gather_rows(x2d.contiguous(), gather_ids[rank])
+        everyone = _all_gather_rows(mine, group, world)
+        return ops.scatter_rows(everyone, scatter_ids, n_rows + 1)[:n_rows]   # last row swallows pad / dummy slots
+    mine = x2d.index_select(0, gather_ids[rank])              # CPU tensors (the gloo tests of the host-side plumbing)
     everyone = _all_gather_rows(mine, group, world)
-    out = x2d.new_empty((n_rows + 1, x2d.shape[1]))                       # last row swallows pad / dummy slots
+    out = x2d.new_empty((n_rows + 1, x2d.shape[1]))
     out.index_copy_(0, scatter_ids, everyone)
     return out[:n_rows]
 

@@ -308,3 +308,24 @@ def test_window_attention_full_size_properties(case):
     total_dv = g[..., 2 * C:].sum(dim=tuple(range(len(grid) + 1))) + bias.grad[2 * C:]
     total_do = d_out.float().sum(dim=tuple(range(len(grid) + 1)))
     assert max_rel(total_dv.cpu(), total_do.cpu()) < 2e-2
+
+
+def test_row_gather_scatter_match_torch_indexing():
+    """csrc/row_copy.cu (the window-sharded exchange) against index_select / index_copy_, incl. 96-byte rows (cfg4 'unetr'
+    output rows) and the dump-row convention of window_parallel._exchange_disjoint_rows."""
+    from long_context_biomedical_imaging_b200 import ops
+
+    torch.manual_seed(4)
+    for rows, feat, dtype in ((1000, 48, torch.bfloat16), (777, 144, torch.bfloat16), (64, 8, torch.float32)):
+        src = torch.randn(rows, feat, device="cuda").to(dtype)
+        ids = torch.randint(0, rows, (rows + 13,), device="cuda")
+        assert torch.equal(ops.gather_rows(src, ids), src.index_select(0, ids))
+        perm = torch.randperm(rows, device="cuda")
+        dump = torch.cat([perm, torch.full((5,), rows, device="cuda", dtype=torch.int64)])      # 5 rows into the dump row
+        packed = torch.randn(rows + 5, feat, device="cuda").to(dtype)
+        got = ops.scatter_rows(packed, dump, rows + 1)[:rows]
+        want = torch.empty(rows, feat, device="cuda", dtype=dtype)
+        want.index_copy_(0, perm, packed[:rows])
+        assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        ops.gather_rows(torch.randn(4, 3, device="cuda"), torch.zeros(2, dtype=torch.int64, device="cuda"))   # 12-byte rows
