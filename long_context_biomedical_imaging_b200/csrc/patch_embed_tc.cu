@@ -15,14 +15,18 @@
 //   2. pe_gemm_kernel    persistent TMA-fed GEMM, one CTA per SM, tile = 128 patches x 128 features, K in blocks of 64
 //                        through a 3-stage ring of (A_hi, A_lo, W_hi, W_lo) SWIZZLE_128B tiles:
 //        warp 0       TMA producer          warp 1   UMMA issuer (4 k-steps x 3 products per k-block, two TMEM accumulators)
-//        warps 4-7    epilogue: TMEM -> + bias (+ position embedding) -> fp32 / bf16 rows of `out`, overlapping the next tile
+//        warps 4-11   epilogue: TMEM -> 32 x 16 transposes through padded shared memory -> + bias (+ position embedding,
+//                     prefetched before the accumulator wait) -> 64-byte row segments of `out`, overlapping the next tile
+//   Backward (dW, dbias): pe_split_kernel again, pe_split_dout_kernel (dOut -> G_hi, G_lo and the column sums), and
+//   pe_bwd_w_gemm_kernel (both operands MN-major, M split over the CTAs, fp32 reductions into dW) - see below.
 // Two fused single-kernel versions were measured first at cfg3 (B = 16): one TMA box per patch and k-block straight from
 // the image with converter warps in between took 368 us (the TMA unit paced by 256-byte boxes of 32-byte runs), one box
 // per patch ROW 245 us (2-stage TMA -> convert -> MMA chain, latency-bound, and every feature tile re-converts its
 // patches: 6x at N = 768). Splitting once costs one extra round trip of the image through HBM (27 us) and wins: 27 + 62 us.
 // The GEMM is bound by shared-memory bandwidth, not by the tensor pipe's arithmetic: a 128x128x16 SS MMA reads 8 KB of
-// operands in its 64 cycles (the full 128 B/clk) while TMA refills 64 KB per k-block - ncu shows the tensor pipe "active"
-// for the whole kernel at half its rate. The next step is a cta_group::2 256x256 tile (each SM streams half of B).
+// operands in its 64 cycles (the full 128 B/clk) while TMA refills 64 KB per k-block - the hmma sub-pipe counter reads as
+// occupied for the whole kernel although the MMAs need half of it (profiles/r02_ncu_pe_gemm_summary.txt). The next step is
+// a 128 x 256 or cta_group::2 256 x 256 tile (12 KB of operand reads per 128-cycle MMA: 96 B/clk).
 #include "lcbi_kernels.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
