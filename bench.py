@@ -459,6 +459,16 @@ def workload_swin(name, dist, rank, world, dev, steps=30, warmup=5):
     per_gpu_share = 1.0 if (weak or not sharded) else 1.0 / world
     alg_bytes = 24.0 * C * n_tok * per_gpu_share       # q,k,v,o read/written fwd + bwd, this GPU's share
     gbs = alg_bytes / (ms * 1e-3) / 1e9
+    # second floor: the exponentials. One exp per (query, key) pair and head in the forward, and one per recompute in the
+    # backward (the generic large-window backward recomputes P in both of its kernels, the small-window one once), on the
+    # MUFU pipe at 16 per clock and SM (sm_100a). At n = 343, d = 16 this floor is above the HBM one.
+    n_win_tok = 1
+    for w_ in window:
+        n_win_tok *= w_
+    props = torch.cuda.get_device_properties(dev)
+    exps = float(n_tok) * n_win_tok * H * (3 if name == "cfg4" else 2) * per_gpu_share
+    clock_khz = float(getattr(props, "clock_rate", 1965000) or 1965000)
+    exp_floor_ms = exps / (props.multi_processor_count * 16.0 * clock_khz * 1e3) * 1e3
     out = {"workload": what,
            "parallelism": (f"batch-sharded x{world} (no data-path collective)" if weak else
                            (f"windows sharded x{world} (window_parallel.py)" if sharded else "one GPU")),
@@ -471,7 +481,11 @@ def workload_swin(name, dist, rank, world, dev, steps=30, warmup=5):
                         "traffic_unit": "bytes per step on one GPU (dram read + write of the fwd + bwd window kernels, one ncu "
                                         "--set full capture each: profiles/r02_ncu_cfg2_small_final_summary.csv, "
                                         "r02_ncu_cfg4_final_summary.csv; the dK/dV kernel after the heads-fastest CTA order)",
-                        "algorithmic_bytes_per_step_per_gpu": alg_bytes},
+                        "algorithmic_bytes_per_step_per_gpu": alg_bytes,
+                        "exp_pipe_floor": {"exps_per_step_per_gpu": exps, "floor_ms": exp_floor_ms,
+                                           "frac": exp_floor_ms / ms,
+                                           "note": "MUFU ex2 at 16 / clk / SM and the device's max SM clock; the "
+                                                   "binding floor when it exceeds algorithmic_bytes / peak"}},
            "gpu_launches_per_step_per_rank": 4}
     if n1_ms is not None:
         out["n1_ms_per_step_same_run"] = n1_ms
