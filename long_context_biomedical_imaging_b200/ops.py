@@ -529,10 +529,15 @@ def _row_args(x2d, ids):
     return dev, row_bytes
 
 
-def gather_rows(src, ids):
-    """out[i] = src[ids[i]] (no autograd: the callers are autograd Functions)."""
+def gather_rows(src, ids, out=None):
+    """out[i] = src[ids[i]] (no autograd: the callers are autograd Functions). `out`: a contiguous (len(ids), F) tensor
+    of src's dtype on the same device to write into."""
     dev, row_bytes = _row_args(src, ids)
-    out = torch.empty((ids.numel(), src.shape[1]), dtype=src.dtype, device=dev)
+    if out is None:
+        out = torch.empty((ids.numel(), src.shape[1]), dtype=src.dtype, device=dev)
+    elif (out.device != dev or out.dtype != src.dtype or tuple(out.shape) != (ids.numel(), src.shape[1])
+          or not out.is_contiguous()):
+        raise ValueError("gather_rows: out must be a contiguous (len(ids), F) tensor of src's dtype and device")
     with _on(dev):
         rc = _lib.load().lcbi_gather_rows(_p(src), _p(ids), _p(out), ids.numel(), row_bytes, _stream(dev))
     _lib.check(rc, "lcbi_gather_rows")

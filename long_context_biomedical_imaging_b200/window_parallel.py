@@ -115,66 +115,116 @@ def _all_gather_rows(rows, group, world):
     return out
 
 
-def _exchange_disjoint_rows(x2d, ids, n_rows, rank, group, world):
+_EXT_IDS_CACHE = {}
+
+
+def _scatter_ids_with_tail(scatter_ids, world, tail_rows, n_rows):
+    """scatter ids of the gathered buffer when every rank's chunk carries `tail_rows` extra rows behind its window rows:
+    those rows are sent to the dump row (index n_rows) like the pad / dummy slots."""
+    if tail_rows == 0:
+        return scatter_ids
+    key = (scatter_ids.data_ptr(), world, tail_rows)
+    hit = _EXT_IDS_CACHE.get(key)
+    if hit is None:
+        per = scatter_ids.numel() // world
+        ext = torch.full((world, per + tail_rows), n_rows, dtype=scatter_ids.dtype, device=scatter_ids.device)
+        ext[:, :per] = scatter_ids.view(world, per)
+        hit = (ext.reshape(-1), scatter_ids)          # keeps scatter_ids alive so that its data_ptr stays unique
+        if len(_EXT_IDS_CACHE) > 64:
+            _EXT_IDS_CACHE.clear()
+        _EXT_IDS_CACHE[key] = hit
+    return hit[0]
+
+
+def _exchange_disjoint_rows(x2d, ids, n_rows, rank, group, world, extra=None):
     """x2d: (n_rows, F) whose rows owned by this rank are valid. Returns the (n_rows, F) tensor in which every rank's
-    owned rows are filled in: gather own rows -> all-gather -> scatter by token id. ids = (gather_ids, scatter_ids)."""
+    owned rows are filled in: pack own rows -> ONE all-gather -> scatter by token id. ids = (gather_ids, scatter_ids).
+    `extra` (a flat float tensor, e.g. this rank's partial parameter gradients) travels in the same all-gather as whole
+    extra rows behind the rank's window rows; the sum over the ranks is returned as the second value."""
     gather_ids, scatter_ids = ids
-    if x2d.is_cuda and (x2d.shape[1] * x2d.element_size()) % 16 == 0:
+    feat, row_bytes = x2d.shape[1], x2d.shape[1] * x2d.element_size()
+    my_ids = gather_ids[rank]
+    n = my_ids.numel()
+    extra_bytes = 0 if extra is None else extra.numel() * extra.element_size()
+    # the tail starts at a 16-byte aligned row boundary: round the rows up when a row is not a multiple of 16 bytes
+    head_rows = n
+    while (head_rows * row_bytes) % 16:
+        head_rows += 1
+    tail_rows = -(-extra_bytes // row_bytes)
+    send = torch.empty((head_rows + tail_rows, feat), dtype=x2d.dtype, device=x2d.device)
+    fast = x2d.is_cuda and row_bytes % 16 == 0
+    if fast:
         # streaming row copies (csrc/row_copy.cu): torch's index_select / index_copy_ ran at ~0.2 TB/s on these rows and
         # were a quarter of the sharded step at cfg4 stage 1
         from . import ops
-        mine = ops.gather_rows(x2d.contiguous(), gather_ids[rank])
-        everyone = _all_gather_rows(mine, group, world)
-        return ops.scatter_rows(everyone, scatter_ids, n_rows + 1)[:n_rows]   # last row swallows pad / dummy slots
-    mine = x2d.index_select(0, gather_ids[rank])              # CPU tensors (the gloo tests of the host-side plumbing)
-    everyone = _all_gather_rows(mine, group, world)
-    out = x2d.new_empty((n_rows + 1, x2d.shape[1]))
-    out.index_copy_(0, scatter_ids, everyone)
-    return out[:n_rows]
+        ops.gather_rows(x2d.contiguous(), my_ids, out=send[:n])
+    else:                                     # CPU tensors (the gloo tests of the host-side plumbing)
+        torch.index_select(x2d, 0, my_ids, out=send[:n])
+    if extra is not None:
+        send.view(-1).view(torch.uint8)[head_rows * row_bytes:head_rows * row_bytes + extra_bytes].view(extra.dtype).copy_(extra)
+    everyone = _all_gather_rows(send, group, world)                      # (world * (head_rows + tail_rows), F)
+    ext_ids = scatter_ids
+    if head_rows + tail_rows != n:
+        if head_rows != n:                    # (odd row sizes: CPU tests only) drop the alignment rows first
+            everyone = everyone.view(world, head_rows + tail_rows, feat)
+            everyone = torch.cat([everyone[:, :n], everyone[:, head_rows:]], 1).reshape(-1, feat)
+        ext_ids = _scatter_ids_with_tail(scatter_ids, world, tail_rows, n_rows)
+    if fast:
+        out = ops.scatter_rows(everyone, ext_ids, n_rows + 1)[:n_rows]   # last row swallows pad / dummy / tail rows
+    else:
+        out = x2d.new_empty((n_rows + 1, feat))
+        out.index_copy_(0, ext_ids, everyone)
+        out = out[:n_rows]
+    if extra is None:
+        return out, None
+    tails = everyone.view(world, n + tail_rows, feat)[:, n:].reshape(world, -1).view(torch.uint8)[:, :extra_bytes]
+    return out, tails.contiguous().view(extra.dtype).view(world, -1).sum(0)
 
 
-class _ReplicatedRows(torch.autograd.Function):
-    """Identity on the replicated qkv; the gradient rows each rank produced (those of its windows) are all-gathered."""
+class _ShardedWindowAttention(torch.autograd.Function):
+    """The whole sharded block as ONE autograd node: forward = range attention on this rank's windows + one all-gather of
+    the owned output rows; backward = range backward + one all-gather that carries the owned dqkv rows AND the rank's
+    partial gradients of the two small parameters (qkv.bias through the pad tokens, the relative-position table), which
+    every rank then sums locally - no separate all-reduce (265 us of a 1.17 ms step at 8 GPUs)."""
 
     @staticmethod
-    def forward(ctx, x, ids, n_rows, rank, group, world):
+    def forward(ctx, qkv, qkv_bias, table, attn_fn, call, ids, n_rows, rank, group, world):
+        inputs = [qkv, qkv_bias, table]
+        local = [None if t is None else t.detach().requires_grad_(t.requires_grad) for t in inputs]
+        with torch.enable_grad():
+            part = attn_fn(local[0], local[1], local[2], *call[0], **call[1])
+        full, _ = _exchange_disjoint_rows(part.detach().reshape(n_rows, part.shape[-1]), ids, n_rows, rank, group, world)
+        ctx.local, ctx.part = local, part
         ctx.meta = (ids, n_rows, rank, group, world)
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        ids, n_rows, rank, group, world = ctx.meta
-        full = _exchange_disjoint_rows(g.reshape(n_rows, g.shape[-1]), ids, n_rows, rank, group, world)
-        return full.reshape(g.shape), None, None, None, None, None
-
-
-class _ReplicatedInput(torch.autograd.Function):
-    """Identity on a small tensor every rank holds a copy of; its gradient is the sum of the ranks' partial gradients."""
-
-    @staticmethod
-    def forward(ctx, x, group):
-        ctx.group = group
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        g = g.contiguous()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        return g, None
-
-
-class _GatherOutputs(torch.autograd.Function):
-    """Partial output (own windows' rows valid) -> full output on every rank. The incoming gradient is replicated and
-    the range backward reads only its own windows' rows of it, so it is passed through unchanged."""
-
-    @staticmethod
-    def forward(ctx, part, ids, n_rows, rank, group, world):
-        full = _exchange_disjoint_rows(part.reshape(n_rows, part.shape[-1]), ids, n_rows, rank, group, world)
         return full.reshape(part.shape)
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None, None, None, None
+        ids, n_rows, rank, group, world = ctx.meta
+        local, part = ctx.local, ctx.part
+        ctx.local = ctx.part = None
+        wanted = [t for t in local if t is not None and t.requires_grad]
+        grads = iter(torch.autograd.grad(part, wanted, g.reshape(part.shape), allow_unused=True)) if wanted else iter(())
+        got = [next(grads) if (t is not None and t.requires_grad) else None for t in local]
+        dqkv, dbias, dtable = got
+        small = [x for x in (dbias, dtable) if x is not None]
+        wide = torch.float64 if any(x.dtype == torch.float64 for x in small) else torch.float32
+        extra = torch.cat([x.reshape(-1).to(wide) for x in small]) if small else None
+        out = [None, None, None]
+        if dqkv is not None:
+            full, total = _exchange_disjoint_rows(dqkv.reshape(n_rows, dqkv.shape[-1]), ids, n_rows, rank, group, world, extra)
+            out[0] = full.reshape(dqkv.shape)
+        elif extra is not None:                               # parameters only (qkv detached): plain all-reduce
+            total = extra.clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        else:
+            total = None
+        offset = 0
+        for i, x in ((1, dbias), (2, dtable)):
+            if x is not None:
+                out[i] = total[offset:offset + x.numel()].view(x.shape).to(x.dtype)
+                offset += x.numel()
+        return out[0], out[1], out[2], None, None, None, None, None, None, None
 
 
 def window_attention_sharded(qkv, qkv_bias, table, grid, window, shift, num_heads, scale=None, group=None, attn_fn=None):
@@ -193,13 +243,5 @@ def window_attention_sharded(qkv, qkv_bias, table, grid, window, shift, num_head
     begin, count = shard_range(total, world, rank)
     g_ids, s_ids, n_rows = _row_ids(batch, grid, tuple(int(w) for w in window), tuple(int(s) for s in shift), world,
                                     qkv.device)
-    ids = (g_ids, s_ids)
-    qkv_r = _ReplicatedRows.apply(qkv, ids, n_rows, rank, group, world)
-    if qkv_bias is not None:                 # one all-reduce for both small parameter gradients
-        packed = _ReplicatedInput.apply(torch.cat([qkv_bias.reshape(-1), table.reshape(-1).to(qkv_bias.dtype)]), group)
-        bias_r = packed[:qkv_bias.numel()].reshape(qkv_bias.shape)
-        table_r = packed[qkv_bias.numel():].reshape(table.shape).to(table.dtype)
-    else:
-        bias_r, table_r = None, _ReplicatedInput.apply(table, group)
-    part = attn_fn(qkv_r, bias_r, table_r, grid, window, shift, num_heads, scale, win_range=(begin, count))
-    return _GatherOutputs.apply(part, ids, n_rows, rank, group, world)
+    call = ((grid, window, shift, num_heads, scale), {"win_range": (begin, count)})
+    return _ShardedWindowAttention.apply(qkv, qkv_bias, table, attn_fn, call, (g_ids, s_ids), n_rows, rank, group, world)
