@@ -4,14 +4,15 @@ The windows of one W-MSA / SW-MSA block are independent, so the flattened (batch
 the ranks of a process group: every rank holds the full (replicated) qkv of the block and runs the fused kernel on its
 window range only (`ops.window_attention(..., win_range=...)`, C ABI `lcbi_win_attn_{fwd,bwd}_range`). Every token
 belongs to exactly one window, so the ranks' results are DISJOINT token rows: they are exchanged with ONE all-gather of
-the owned rows (window-major, 1/P of the tensor per rank) followed by a scatter to token order — not an all-reduce of
-the zero-padded full tensor, which moves twice the bytes. Backward mirrors it: the incoming gradient is replicated,
-every rank back-propagates through its windows, the dqkv rows (disjoint again) are all-gathered, and the two small
-parameter gradients (qkv.bias through the pad tokens, the relative-position table) share one all-reduce.
+the owned rows (packed window-major by `lcbi_gather_rows`, 1/P of the tensor per rank) followed by a scatter to token
+order (`lcbi_scatter_rows`) — not an all-reduce of the zero-padded full tensor, which moves twice the bytes. Backward
+mirrors it inside the same autograd node: the incoming gradient is replicated, every rank back-propagates through its
+windows, and one all-gather carries the dqkv rows (disjoint again) together with the rank's partial gradients of the
+two small parameters (qkv.bias through the pad tokens, the relative-position table), which are then summed locally.
 
 Consecutive blocks use different (shifted) partitions, so tokens must be visible to every rank between blocks: this is
-the simple formulation of 8e (a). Per-GPU compute at cfg4 stage 1 is of the order of 100 microseconds, so collective
-latency and not the kernels bounds this configuration - bench.py reports it as measured.
+the simple formulation of 8e (a). Per-GPU compute at cfg4 stage 1 is of the order of 200 microseconds at 8 GPUs, so
+collective latency and not the kernels bounds this configuration - bench.py reports it as measured.
 """
 from __future__ import annotations
 
