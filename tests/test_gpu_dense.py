@@ -256,6 +256,58 @@ def test_patch_embed_workspace_contract_through_the_c_abi():
         assert rc != 0 and b"workspace" in lib.lcbi_last_error()
 
 
+def test_patch_embed_streaming_kernels_random_geometries():
+    """K in {4, 8, 16} streaming forward / narrow-row backward against F.conv over random image sizes (with and without
+    trailing pad), patch shapes, channel counts and feature widths: catches index-map slips the named configs miss."""
+    import random
+
+    import torch.nn.functional as F
+    from long_context_biomedical_imaging_b200 import ops
+
+    rng = random.Random(7)
+    patches = [(1, 2, 2), (1, 4, 4), (1, 2, 4), (1, 4, 2), (2, 2, 2), (2, 2, 4), (1, 1, 4), (4, 2, 2), (1, 2, 8), (1, 4, 1)]
+    for trial in range(14):
+        patch = rng.choice(patches)
+        cin = rng.choice([1, 1, 2, 4])
+        k = cin * patch[0] * patch[1] * patch[2]
+        if k not in (4, 8, 16):
+            continue
+        dims = tuple(p * rng.randint(2, 40 if i == 2 else 6) + (rng.randint(0, p - 1) if rng.random() < 0.5 else 0)
+                     for i, p in enumerate(patch))
+        if patch[0] == 1:
+            dims = (1,) + dims[1:]
+        hidden = rng.choice([8, 24, 48, 96, 132, 256, 320])
+        B = rng.randint(1, 3)
+        vit = rng.random() < 0.5
+        torch.manual_seed(trial)
+        x = torch.randn(B, cin, *dims, device="cuda")
+        w = (torch.randn(hidden, cin, *patch, device="cuda") * 0.3).requires_grad_(True)
+        b = torch.randn(hidden, device="cuda", requires_grad=True)
+        grid = [-(-s_ // p_) for s_, p_ in zip(dims, patch)]
+        pos = torch.randn(1, grid[0] * grid[1] * grid[2], hidden, device="cuda", requires_grad=True) if vit else None
+        y = ops.patch_embed(x, w, b, pos, grid, torch.float32)
+        pads = []
+        for s_, p_ in zip(reversed(dims), reversed(patch)):
+            pads += [0, (p_ - s_ % p_) % p_]
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            ref = F.conv3d(F.pad(x, pads).double(), w.double(), b.double(), stride=patch).flatten(2).transpose(1, 2)
+            if pos is not None:
+                ref = ref + pos.double()
+            dout = torch.randn(ref.shape, device="cuda")
+            grads = torch.autograd.grad(ref, (w, b) + ((pos,) if vit else ()), dout.double())
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        tag = (trial, patch, cin, dims, hidden, B, vit)
+        assert max_rel(y.detach().cpu(), ref.detach().float().cpu()) < FP32_TOL, tag
+        y.backward(dout)
+        assert max_rel(w.grad.cpu(), grads[0].float().cpu()) < FP32_TOL, tag
+        assert max_rel(b.grad.cpu(), grads[1].float().cpu()) < FP32_TOL, tag
+        if vit:
+            assert max_rel(pos.grad.cpu(), grads[2].float().cpu()) < FP32_TOL, tag
+
+
 def _vit_cfg(hidden, mlp, layers, heads, patch, t, h, w, task="seg"):
     return types.SimpleNamespace(ViT=types.SimpleNamespace(size="custom", hidden_size=hidden, mlp_dim=mlp, num_layers=layers,
                                                            num_heads=heads, patch_size=list(patch), use_hyena=False,
