@@ -727,8 +727,10 @@ win_attn_bwd_dq_kernel(const WinParams p) {
       }
       const bool tail = key0 + 32 > n;           // only then can a key column be a dead slot
       const float2 neg_lse = make_float2(-lse0, -lse1), neg_ds = make_float2(-ds0, -ds1);
-      auto grads = [&](auto masked_c) {
+      // the dead-slot test of a key column is compiled only into the one 32-key step that holds the window's last keys
+      auto grads = [&](auto masked_c, auto tail_c) {
         constexpr bool kMasked = decltype(masked_c)::value;
+        constexpr bool kTail = decltype(tail_c)::value;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int j = key0 + nt * 8 + qq * 2;
@@ -749,7 +751,7 @@ win_attn_bwd_dq_kernel(const WinParams p) {
               l = fadd2(l, make_float2(rg0 != rje ? mask_log2 : 0.f, rg1 != rje ? mask_log2 : 0.f));
             }
             float2 d = fmul2(make_float2(ex2f(l.x), ex2f(l.y)), fadd2(make_float2(dp[nt][e], dp[nt][2 + e]), neg_ds));
-            if (tail && j + e >= n) d = make_float2(0.f, 0.f);
+            if (kTail && j + e >= n) d = make_float2(0.f, 0.f);
             dp[nt][e] = d.x;
             dp[nt][2 + e] = d.y;
             const float2 db = fadd2(make_float2(dbias[sub * 4 + nt][e], dbias[sub * 4 + nt][2 + e]), d);
@@ -758,7 +760,11 @@ win_attn_bwd_dq_kernel(const WinParams p) {
           }
         }
       };
-      if (has_mask) grads(std::true_type{}); else grads(std::false_type{});
+      if (tail) {
+        if (has_mask) grads(std::true_type{}, std::true_type{}); else grads(std::false_type{}, std::true_type{});
+      } else {
+        if (has_mask) grads(std::true_type{}, std::false_type{}); else grads(std::false_type{}, std::false_type{});
+      }
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         uint32_t ads[4];
